@@ -1,0 +1,85 @@
+// Implicit-GEMM plans for the tcgen05 kernels in igemm.cu.
+//
+// One kernel family covers dense layers, 1x1 / 3x3 / strided convolutions,
+// their data gradients (and therefore transposed convolutions) and their
+// weight gradients: the A operand is always fetched by TMA from a 4-D tiled
+// tensor map (C, W, H, N) whose out-of-bounds zero fill supplies the conv halo,
+// a filter tap is a coordinate shift of the TMA box, and the K loop walks
+// (tap, channel-chunk) pairs.  Python (ops/conv.py) decides boxes and taps;
+// this header is the contract between that code and the kernels.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tfos {
+
+constexpr int kMaxTaps = 9;
+
+// Host-side description of one tiled tensor map (bf16 elements, SWIZZLE_128B,
+// zero OOB fill).  rank is 2 or 4; dim0 is the contiguous (channel) dimension.
+struct TmapDesc {
+  void* base;
+  int rank;
+  uint64_t dims[4];
+  uint64_t strides_bytes[3];  // strides of dims 1..rank-1
+  uint32_t box[4];
+  uint32_t elem_strides[4];
+};
+
+// "forward-like" problems: M = pixels.  Used by fprop, dgrad, convT and GEMM.
+struct FwdArgs {
+  int tiles_w, tiles_h, tiles_n, n_tiles;
+  int box_w, box_h, box_n;  // A box extents in pixels; rows = product <= 128
+  int mul_w, mul_h;         // tile origin -> A coordinate multiplier (conv stride)
+  int num_taps, k_chunks;   // K loop = num_taps * k_chunks blocks of 64 channels
+  int tap_dw[kMaxTaps], tap_dh[kMaxTaps], tap_dc[kMaxTaps];
+  int tap_bk[kMaxTaps];     // K offset of the tap inside the B matrix
+  int tap_bn[kMaxTaps];     // N (column) offset of the tap, MN-major B only (dgrad)
+  int lim_w, lim_h, lim_n;  // valid extents in tile coordinates
+  int OW, OH;               // full output tensor extents (addressing)
+  int osw, oow, osh, ooh;   // output pixel = tile pixel * os + oo (strided dgrad)
+  int ldo;                  // output row pitch in elements
+  int n_valid;              // valid output columns
+  int relu, out_fp32, accumulate;
+  const float* bias;        // per-output-column, may be null
+  float* col_sum;           // optional fused per-column sum / sum of squares
+  float* col_sumsq;         //   (batch-norm statistics of the stored tensor)
+  void* out;
+};
+
+// weight-gradient problems: K = pixels, M = Cout, N = Cin (per tap).
+struct WgradArgs {
+  int tiles_w, tiles_h, tiles_n;  // pixel boxes
+  int box_rows;                   // pixels per box, multiple of 16, <= 128
+  int box_w, box_h, box_n;
+  int mul_w, mul_h;               // B (activation) coordinate multiplier
+  int num_taps;
+  int tap_dw[kMaxTaps], tap_dh[kMaxTaps], tap_dc[kMaxTaps];
+  int tap_out[kMaxTaps];          // element offset of the tap inside a dW row
+  int m_tiles, n_tiles, k_splits;
+  int m_valid, n_valid;           // Cout, Cin
+  int ldw;                        // dW row pitch in elements (= taps * Cin)
+  float* dw;                      // fp32, accumulated with red.global.add
+};
+
+struct IGemmPlan {
+  CUtensorMap tmA, tmB;
+  FwdArgs fa;
+  WgradArgs wa;
+  int kind;  // 0 = fwd-like, 1 = wgrad
+  int bn;    // 64 / 128 / 256
+  int b_mn;  // fwd-like only: B is MN-major ([K rows, N cols])
+  int grid;
+  int total_work;
+};
+
+// Returns nullptr and fills err on failure.
+IGemmPlan* igemm_plan_fwd(const TmapDesc& a, const TmapDesc& b, const FwdArgs& args, int bn,
+                          int b_mn, int num_sms, char* err, int errlen);
+IGemmPlan* igemm_plan_wgrad(const TmapDesc& a, const TmapDesc& b, const WgradArgs& args, int bn,
+                            int num_sms, char* err, int errlen);
+cudaError_t igemm_run(const IGemmPlan* plan, cudaStream_t stream);
+void igemm_plan_free(IGemmPlan* plan);
+
+}  // namespace tfos

@@ -1,0 +1,95 @@
+// C++ entry points of the non-GEMM sm_100a kernels (elementwise.cu,
+// optim_comm.cu, feed.cu).  All functions enqueue on the given stream and
+// return the launch status; none of them synchronises.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tfos {
+
+// ---- elementwise.cu
+cudaError_t bn_stats(const void* x, long long P, int C, float* sum, float* sumsq, cudaStream_t s);
+cudaError_t bn_finalize(float* sum, float* sumsq, const float* gamma, const float* beta,
+                        float* running_mean, float* running_var, float* mean, float* invstd,
+                        float* scale, float* shift, int C, float count, float eps, float momentum,
+                        cudaStream_t s);
+cudaError_t bn_inference_coeffs(const float* gamma, const float* beta, const float* rm,
+                                const float* rv, float* scale, float* shift, int C, float eps,
+                                cudaStream_t s);
+cudaError_t bn_apply(const void* x, const void* residual, const float* scale, const float* shift,
+                     void* y, long long P, int C, int act, cudaStream_t s);
+cudaError_t bn_bwd_reduce(const void* dy, const void* x, const void* y, const float* mean,
+                          const float* invstd, long long P, int C, int relu, float* dgamma,
+                          float* dbeta, cudaStream_t s);
+cudaError_t bn_bwd_apply(const void* dy, const void* x, const void* y, const float* gamma,
+                         const float* mean, const float* invstd, const float* dgamma,
+                         const float* dbeta, void* dx, void* dres, long long P, int C, int relu,
+                         cudaStream_t s);
+cudaError_t add_act(const void* a, const void* b, void* out, long long n, int act, cudaStream_t s);
+cudaError_t relu_bwd(const void* dy, const void* y, void* dx, long long n, cudaStream_t s);
+cudaError_t colsum(const void* x, long long P, int C, float* out, cudaStream_t s);
+cudaError_t maxpool_fwd(const void* x, void* y, uint8_t* idx, int N, int H, int W, int C, int OH,
+                        int OW, int k, int stride, int pad, cudaStream_t s);
+cudaError_t maxpool_bwd(const void* dy, const uint8_t* idx, void* dx, int N, int H, int W, int C,
+                        int OH, int OW, int k, int stride, int pad, cudaStream_t s);
+cudaError_t avgpool_fwd(const void* x, void* y, int N, int HW, int C, cudaStream_t s);
+cudaError_t avgpool_bwd(const void* dy, void* dx, int N, int HW, int C, cudaStream_t s);
+cudaError_t softmax_xent(const void* logits, int logits_fp32, const int* labels, void* dlogits,
+                         float* loss_sum, float* correct_sum, long long rows, int V, int ld,
+                         int ldd, float scale, cudaStream_t s);
+cudaError_t decode_normalize(const uint8_t* in, void* out, int N, int H, int W, int C, int Wp,
+                             int Cp, int wofs, const float* mean3, const float* istd3,
+                             cudaStream_t s);
+cudaError_t cast_f32_bf16(const float* in, void* out, long long n, cudaStream_t s);
+
+// ---- optim_comm.cu
+constexpr int kMaxRanks = 8;
+constexpr int kOptSgd = 0, kOptMomentum = 1, kOptAdam = 2;
+
+struct AllreduceOptArgs {
+  float* master;       // fp32 master weights (full length; a rank only touches its shards)
+  float* state1;       // momentum / Adam m
+  float* state2;       // Adam v
+  const float* hyper;  // device: lr, momentum, wd, grad_scale, beta1, beta2, eps, step
+  long long begin, end;  // element range of this bucket (begin % 8 == 0)
+  long long decay_end;   // elements [0, decay_end) receive weight decay
+  long long state_offset;
+  int world, rank, slot, zero_grads;
+  float* grads[kMaxRanks];             // every rank's fp32 gradient buffer (peer-mapped)
+  __nv_bfloat16* weights[kMaxRanks];   // every rank's bf16 weight buffer (peer-mapped)
+  uint32_t* flags[kMaxRanks];          // every rank's flag pad (peer-mapped)
+  float* aux32[kMaxRanks];             // every rank's fp32 replica of elements >= aux_begin
+  long long aux_begin;                 //   (BN scale/offset, biases); may be null
+  const float* grads_mc;               // NVLS multicast views (optional)
+  __nv_bfloat16* weights_mc;
+  uint32_t* epoch;          // local, one word per slot
+  uint32_t* block_counter;  // local, one word per slot
+};
+cudaError_t allreduce_opt(const AllreduceOptArgs& a, int opt, int grid, cudaStream_t s);
+
+struct BcastArgs {
+  int world, rank, root, slot;
+  long long bytes;
+  void* bufs[kMaxRanks];
+  uint32_t* flags[kMaxRanks];
+  uint32_t* epoch;
+  uint32_t* block_counter;
+};
+cudaError_t bcast_pull(const BcastArgs& a, int grid, cudaStream_t s);
+cudaError_t flag_barrier(const BcastArgs& a, cudaStream_t s);
+cudaError_t ps_push_dense(float* w_ps, const float* g, long long n, const float* hyper,
+                          cudaStream_t s);
+cudaError_t ps_push_sparse(float* w_ps, const float* g_rows, const int* idx, int nrows, int width,
+                           const float* hyper, cudaStream_t s);
+cudaError_t ps_pull(const float* w_ps, float* w_local, void* w_bf16, long long n, cudaStream_t s);
+
+// ---- small direct kernels (smallops.cu): MNIST conv (Cin=1), depthwise 3x3
+cudaError_t conv3x3_c1_fwd(const void* x, const void* w, const float* bias, void* y, int N, int H,
+                           int W, int Cout, int relu, cudaStream_t s);
+cudaError_t conv3x3_c1_wgrad(const void* x, const void* dy, float* dw, float* dbias, int N, int H,
+                             int W, int Cout, cudaStream_t s);
+cudaError_t depthwise3x3_fwd(const void* x, const void* w, void* y, int N, int H, int W, int C,
+                             int stride, cudaStream_t s);
+
+}  // namespace tfos

@@ -1,0 +1,223 @@
+"""Explicit-graph training engine on the native kernels.
+
+There is no autograd and no tracing compiler here: a model is a list of layer
+objects with static device buffers, ``forward()``/``backward()`` enqueue native
+kernels on the current CUDA stream in a fixed order, and the whole step can be
+captured once into a CUDA graph.  Parameters live in three flat buffers
+(fp32 master, bf16 compute copy, fp32 gradients) so that the data-parallel
+all-reduce and the optimizer are one fused kernel over contiguous ranges
+(parallel/fused_optim.py).
+
+This is the B200-native stand-in for what the reference delegates to Keras /
+tf.distribute in its example programs (e.g. examples/mnist/keras/mnist_spark.py:
+11-66, examples/resnet/resnet_cifar_dist.py:196-257).
+"""
+import math
+
+import torch
+
+from .. import ops
+from ..ops import igemm
+
+
+def _pad8(n):
+  return (n + 7) // 8 * 8
+
+
+class ParamStore(object):
+  """Flat parameter storage.  Decayed parameters (conv / dense weights) come first,
+  then the non-decayed ones (batch-norm scale/offset, biases)."""
+
+  def __init__(self):
+    self._specs = []  # (name, shape, decay, init_fn)
+    self.finalized = False
+
+  def register(self, name, shape, decay, init):
+    assert not self.finalized
+    spec = {"name": name, "shape": tuple(shape), "decay": bool(decay), "init": init}
+    self._specs.append(spec)
+    return spec
+
+  def finalize(self, device, alloc=None, seed=1234):
+    """alloc(nbytes_name, numel, dtype) -> tensor lets the caller place the buffers in
+    symmetric (peer-mapped) memory; default is ordinary device memory."""
+    order = [s for s in self._specs if s["decay"]] + [s for s in self._specs if not s["decay"]]
+    off = 0
+    for s in order:
+      s["offset"] = off
+      s["numel"] = int(math.prod(s["shape"]))
+      off += _pad8(s["numel"])
+    self.decay_end = sum(_pad8(s["numel"]) for s in order if s["decay"])
+    self.total = _pad8(off)
+    self.order = order
+    if alloc is None:
+      alloc = lambda name, n, dt: torch.zeros(n, dtype=dt, device=device)  # noqa: E731
+    self.master = torch.zeros(self.total, dtype=torch.float32, device=device)
+    self.weights = alloc("weights", self.total, torch.bfloat16)
+    self.grads = alloc("grads", self.total, torch.float32)
+    # fp32 replica of the non-decayed tail (BN scale/offset are consumed in fp32)
+    self.aux32 = alloc("aux32", max(8, self.total - self.decay_end), torch.float32)
+    gen = torch.Generator(device="cpu")
+    gen.manual_seed(seed)
+    for s in order:
+      v = s["init"](s["shape"], gen).to(torch.float32).reshape(-1)
+      self.master[s["offset"]:s["offset"] + s["numel"]].copy_(v)
+    self.weights.copy_(self.master)
+    self.aux32[:self.total - self.decay_end].copy_(self.master[self.decay_end:])
+    self.finalized = True
+    self.by_name = {s["name"]: s for s in order}
+
+  def _view(self, buf, s, base=0):
+    return buf[s["offset"] - base:s["offset"] - base + s["numel"]].view(s["shape"])
+
+  def w(self, s):
+    return self._view(self.weights, s)
+
+  def g(self, s):
+    return self._view(self.grads, s)
+
+  def m(self, s):
+    return self._view(self.master, s)
+
+  def f32(self, s):
+    """fp32 value of a non-decayed parameter as seen by every rank."""
+    assert not s["decay"]
+    return self._view(self.aux32, s, self.decay_end)
+
+  def state_dict(self):
+    # master is authoritative only for a rank's own shards when world > 1; the bf16 copy and
+    # aux32 are complete everywhere, so checkpoints are assembled by parallel/fused_optim.py.
+    return {s["name"]: self.m(s).detach().cpu().clone() for s in self.order}
+
+  def load_state_dict(self, sd):
+    for s in self.order:
+      if s["name"] in sd:
+        self.m(s).copy_(sd[s["name"]].to(self.master.device, torch.float32).view(s["shape"]))
+    self.weights.copy_(self.master)
+    self.aux32[:self.total - self.decay_end].copy_(self.master[self.decay_end:])
+
+
+def he_normal(fan_in):
+  std = math.sqrt(2.0 / fan_in)
+  return lambda shape, gen: torch.randn(shape, generator=gen) * std
+
+
+def constant(v):
+  return lambda shape, gen: torch.full(shape, float(v))
+
+
+def normal(std):
+  return lambda shape, gen: torch.randn(shape, generator=gen) * std
+
+
+class BatchNorm(object):
+  """Training-mode batch norm over NHWC bf16 with statistics fused into the producer conv."""
+
+  def __init__(self, store, name, C, eps=1e-5, momentum=0.1, zero_gamma=False):
+    self.C, self.eps, self.momentum, self.name = C, eps, momentum, name
+    self.sg = store.register(name + ".gamma", (C,), False, constant(0.0 if zero_gamma else 1.0))
+    self.sb = store.register(name + ".beta", (C,), False, constant(0.0))
+    self.store = store
+
+  def build(self, device):
+    z = lambda: torch.zeros(self.C, dtype=torch.float32, device=device)  # noqa: E731
+    self.sum, self.sumsq = z(), z()
+    self.mean, self.invstd, self.scale, self.shift = z(), z(), z(), z()
+    self.running_mean = z()
+    self.running_var = torch.ones(self.C, dtype=torch.float32, device=device)
+    self.gamma, self.beta = self.store.f32(self.sg), self.store.f32(self.sb)
+    self.dgamma, self.dbeta = self.store.g(self.sg), self.store.g(self.sb)
+
+  @property
+  def stats(self):
+    return (self.sum, self.sumsq)
+
+  def forward(self, x_raw, y, residual=None, act=1, training=True, fused_stats=True):
+    count = x_raw.numel() // self.C
+    if training:
+      if not fused_stats:
+        ops.K.bn_stats(x_raw, self.sum, self.sumsq)
+      ops.K.bn_finalize(self.sum, self.sumsq, self.gamma, self.beta, self.running_mean,
+                        self.running_var, self.mean, self.invstd, self.scale, self.shift,
+                        float(count), self.eps, self.momentum)
+    else:
+      ops.K.bn_inference_coeffs(self.gamma, self.beta, self.running_mean, self.running_var,
+                                self.scale, self.shift, self.eps)
+    ops.K.bn_apply(x_raw, residual, self.scale, self.shift, y, act)
+
+  def backward(self, dy, x_raw, y, dx, dres=None, relu=True):
+    ops.K.bn_bwd_reduce(dy, x_raw, y if relu else None, self.mean, self.invstd, self.dgamma,
+                        self.dbeta, relu)
+    ops.K.bn_bwd_apply(dy, x_raw, y if relu else None, self.gamma, self.mean, self.invstd,
+                       self.dgamma, self.dbeta, dx, dres, relu)
+
+
+class Conv(object):
+  """Convolution parameters + its three igemm plans (fprop / dgrad / wgrad)."""
+
+  def __init__(self, store, name, cin, cout, k, stride=1, pad=None, bias=False):
+    self.cin, self.cout, self.k, self.stride = cin, cout, k, stride
+    self.pad = (k // 2) if pad is None else pad
+    self.name = name
+    self.store = store
+    self.sw = store.register(name + ".w", (cout, k, k, cin), True, he_normal(k * k * cin))
+    self.sbias = store.register(name + ".b", (cout,), False, constant(0.0)) if bias else None
+
+  def out_hw(self, H, W):
+    return ((H + 2 * self.pad - self.k) // self.stride + 1,
+            (W + 2 * self.pad - self.k) // self.stride + 1)
+
+  def build(self, x, y, dy=None, dx=None, stats=None, relu=False, dx_accumulate=False,
+            need_dgrad=True, training=True):
+    st = self.store
+    self.x, self.y = x, y
+    bias = st.f32(self.sbias) if self.sbias is not None else None
+    self.fwd = igemm.conv_fprop(x, st.w(self.sw), y, self.stride, self.pad, bias=bias, relu=relu,
+                                stats=stats)
+    self.wgrad = self.dgrad = None
+    if training and dy is not None:
+      self.wgrad = igemm.conv_wgrad(dy, x, st.g(self.sw), self.stride, self.pad)
+      if need_dgrad and dx is not None:
+        self.dgrad = igemm.conv_dgrad(dy, st.w(self.sw), dx, self.stride, self.pad,
+                                      accumulate=dx_accumulate)
+    self.dy = dy
+
+  def forward(self):
+    self.fwd.run()
+
+  def backward(self):
+    self.wgrad.run()
+    if self.sbias is not None:
+      ops.K.colsum(self.dy, self.store.g(self.sbias))
+    if self.dgrad is not None:
+      self.dgrad.run()
+
+
+class Dense(object):
+  """Fully connected layer on [B, K] activations (GEMM + bias (+ReLU) epilogue)."""
+
+  def __init__(self, store, name, cin, cout, bias=True, init=None):
+    self.cin, self.cout, self.name, self.store = cin, cout, name, store
+    self.sw = store.register(name + ".w", (cout, cin), True, init or he_normal(cin))
+    self.sbias = store.register(name + ".b", (cout,), False, constant(0.0)) if bias else None
+
+  def build(self, x, y, dy=None, dx=None, relu=False, training=True):
+    st = self.store
+    bias = st.f32(self.sbias) if self.sbias is not None else None
+    self.fwd = igemm.gemm(x, st.w(self.sw), y, "nk", bias=bias, relu=relu)
+    self.wgrad = self.dgrad = None
+    self.dy = dy
+    if training and dy is not None:
+      self.wgrad = igemm.gemm_wgrad(dy, x, st.g(self.sw))
+      if dx is not None:
+        self.dgrad = igemm.gemm(dy, st.w(self.sw), dx, "kn")
+
+  def forward(self):
+    self.fwd.run()
+
+  def backward(self):
+    self.wgrad.run()
+    if self.sbias is not None:
+      ops.K.colsum(self.dy, self.store.g(self.sbias))
+    if self.dgrad is not None:
+      self.dgrad.run()

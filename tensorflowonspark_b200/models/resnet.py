@@ -1,0 +1,274 @@
+"""ResNet (v1.5 bottleneck: 50/101/152; basic-block CIFAR variants 20/32/56) on the
+native engine: NHWC bf16 activations, tcgen05 implicit-GEMM convolutions with
+batch-norm statistics fused into their epilogues, fused BN+ReLU(+residual)
+apply/backward kernels, fused all-reduce + momentum-SGD optimizer.
+
+Workload parity: the reference trains ResNet-56/CIFAR-10 through an external
+Keras model (examples/resnet/resnet_cifar_dist.py:208, momentum SGD with a
+piecewise schedule :35-66); BASELINE.json names ResNet-50/ImageNet-shaped data
+as the headline config.  Both are provided here.
+"""
+import torch
+
+from .. import ops
+from ..ops import igemm
+from .engine import BatchNorm, Conv, Dense, ParamStore, normal
+
+
+class _Unit(object):
+  """conv -> BN (-> +residual) -> ReLU with its forward and gradient buffers."""
+
+  def __init__(self, store, name, cin, cout, k, stride, zero_gamma=False):
+    self.conv = Conv(store, name + ".conv", cin, cout, k, stride)
+    self.bn = BatchNorm(store, name + ".bn", cout, zero_gamma=zero_gamma)
+    self.cout = cout
+
+
+class _Block(object):
+  pass
+
+
+def _buf(shape, device, dtype=torch.bfloat16):
+  return torch.zeros(shape, dtype=dtype, device=device)
+
+
+class ResNetTrainer(object):
+  """Static-buffer ResNet.  ``train_step(images_u8 | normalized, labels)`` runs
+  forward, backward and the fused optimizer; ``forward_only`` serves inference."""
+
+  CFG = {50: (3, 4, 6, 3), 101: (3, 4, 23, 3), 152: (3, 8, 36, 3)}
+
+  def __init__(self, depth=50, batch=256, image=224, num_classes=1000, device="cuda:0",
+               lr=0.1, momentum=0.9, weight_decay=1e-4, comm=None, training=True, seed=1234,
+               optimizer="momentum"):
+    assert depth in self.CFG, "bottleneck depths: 50/101/152"
+    self.device = torch.device(device)
+    self.B, self.image, self.num_classes = batch, image, num_classes
+    self.training = training
+    self.comm = comm
+    dev = self.device
+    st = self.store = ParamStore()
+    B = batch
+
+    # ---- parameters -----------------------------------------------------
+    self.stem_w = st.register("stem.conv.w", (64, 7, 64), True, self._stem_init)
+    self.stem_bn = BatchNorm(st, "stem.bn", 64)
+    self.blocks = []
+    cin = 64
+    for si, nblocks in enumerate(self.CFG[depth]):
+      width = 64 * (2 ** si)
+      for bi in range(nblocks):
+        stride = 2 if (bi == 0 and si > 0) else 1
+        b = _Block()
+        name = "layer{}.{}".format(si + 1, bi)
+        b.u1 = _Unit(st, name + ".u1", cin, width, 1, 1)
+        b.u2 = _Unit(st, name + ".u2", width, width, 3, stride)
+        b.u3 = _Unit(st, name + ".u3", width, width * 4, 1, 1, zero_gamma=True)
+        b.ds = _Unit(st, name + ".ds", cin, width * 4, 1, stride) if bi == 0 else None
+        b.stride, b.cin, b.width = stride, cin, width
+        self.blocks.append(b)
+        cin = width * 4
+    self.fc = Dense(st, "fc", cin, num_classes, bias=True, init=normal(0.01))
+    self.feat = cin
+
+    alloc = comm.alloc if comm is not None else None
+    st.finalize(dev, alloc=alloc, seed=seed)
+
+    # ---- buffers and plans -----------------------------------------------
+    OH, OW, Wp = igemm.stem_geometry(image, image)
+    self.in_u8 = _buf((B, image, image, 3), dev, torch.uint8)
+    self.xp = _buf((B, image, Wp, 8), dev)
+    self.labels = torch.zeros(B, dtype=torch.int32, device=dev)
+    self.stem_raw = _buf((B, OH, OW, 64), dev)
+    self.stem_act = _buf((B, OH, OW, 64), dev)
+    PH, PW = (OH + 2 - 3) // 2 + 1, (OW + 2 - 3) // 2 + 1
+    self.pool = _buf((B, PH, PW, 64), dev)
+    self.pool_idx = _buf((B, PH, PW, 64), dev, torch.uint8)
+    self.stem_bn.build(dev)
+    self.p_stem = igemm.stem_fprop(self.xp, st.w(self.stem_w), self.stem_raw,
+                                   stats=self.stem_bn.stats)
+    tr = training
+    if tr:
+      self.g_stem_act = _buf((B, OH, OW, 64), dev)
+      self.g_stem_raw = _buf((B, OH, OW, 64), dev)
+      self.p_stem_wgrad = igemm.stem_wgrad(self.g_stem_raw, self.xp, st.g(self.stem_w))
+
+    x, H, W = self.pool, PH, PW
+    gx = _buf(x.shape, dev) if tr else None  # gradient wrt the block input
+    self.g_pool = gx
+    for b in self.blocks:
+      s = b.stride
+      H2, W2 = (H - 1) // s + 1, (W - 1) // s + 1
+      w, c4 = b.width, b.width * 4
+      b.x = x
+      b.r1, b.a1 = _buf((B, H, W, w), dev), _buf((B, H, W, w), dev)
+      b.r2, b.a2 = _buf((B, H2, W2, w), dev), _buf((B, H2, W2, w), dev)
+      b.r3, b.out = _buf((B, H2, W2, c4), dev), _buf((B, H2, W2, c4), dev)
+      if tr:
+        b.g_r1, b.g_a1 = _buf(b.r1.shape, dev), _buf(b.a1.shape, dev)
+        b.g_r2, b.g_a2 = _buf(b.r2.shape, dev), _buf(b.a2.shape, dev)
+        b.g_r3 = _buf(b.r3.shape, dev)
+        # identity blocks share the stage gradient buffer: g_out is rewritten in place
+        # into g_x (masked residual gradient + conv1 dgrad accumulated on top)
+        b.g_out = _buf(b.out.shape, dev) if b.ds is not None else gx
+        b.g_x = gx
+      else:
+        b.g_r1 = b.g_a1 = b.g_r2 = b.g_a2 = b.g_r3 = b.g_out = b.g_x = None
+      for u in (b.u1, b.u2, b.u3) + ((b.ds,) if b.ds else ()):
+        u.bn.build(dev)
+      ident = b.ds is None
+      b.u1.conv.build(x, b.r1, b.g_r1, b.g_x, stats=b.u1.bn.stats, dx_accumulate=ident,
+                      training=tr)
+      b.u2.conv.build(b.a1, b.r2, b.g_r2, b.g_a1, stats=b.u2.bn.stats, training=tr)
+      b.u3.conv.build(b.a2, b.r3, b.g_r3, b.g_a2, stats=b.u3.bn.stats, training=tr)
+      if b.ds is not None:
+        b.rd, b.idn = _buf(b.r3.shape, dev), _buf(b.r3.shape, dev)
+        b.g_rd = _buf(b.r3.shape, dev) if tr else None
+        b.ds.conv.build(x, b.rd, b.g_rd, b.g_x, stats=b.ds.bn.stats, dx_accumulate=True,
+                        training=tr)
+      x, H, W = b.out, H2, W2
+      if tr:
+        gx = b.g_out
+    self.last = x
+    self.g_last = gx
+    self.avg = _buf((B, self.feat), dev)
+    self.logits = _buf((B, num_classes), dev, torch.float32)
+    self.ldd = (num_classes + 7) // 8 * 8
+    self.dlogits = _buf((B, self.ldd), dev) if tr else None
+    self.g_avg = _buf((B, self.feat), dev) if tr else None
+    self.loss_sum = torch.zeros(1, dtype=torch.float32, device=dev)
+    self.correct = torch.zeros(1, dtype=torch.float32, device=dev)
+    dl = self.dlogits[:, :num_classes] if (tr and self.ldd == num_classes) else None
+    if tr and dl is None:
+      raise ValueError("num_classes must be a multiple of 8 (pad the head)")
+    self.fc.build(self.avg, self.logits, dl, self.g_avg, training=tr)
+
+    self.optim = None
+    if tr:
+      from ..parallel.fused_optim import FusedOptimizer
+      self.optim = FusedOptimizer(st, comm=comm, opt=optimizer, lr=lr, momentum=momentum,
+                                  weight_decay=weight_decay)
+    self.graph = None
+    self.mean = [0.485, 0.456, 0.406]
+    self.std = [0.229, 0.224, 0.225]
+
+  @staticmethod
+  def _stem_init(shape, gen):
+    import math
+    w = torch.randn((shape[0], 7, 7, 3), generator=gen) * math.sqrt(2.0 / (7 * 7 * 3))
+    return igemm.pack_stem_weight(w)
+
+  # ------------------------------------------------------------------ data
+  def synthetic_batch(self, seed=0):
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed)
+    x = torch.randint(0, 256, (self.B, self.image, self.image, 3), dtype=torch.uint8, generator=g)
+    y = torch.randint(0, self.num_classes, (self.B,), dtype=torch.int32, generator=g)
+    return x.to(self.device), y.to(self.device)
+
+  def set_input(self, images_u8, labels=None):
+    """Stage a uint8 NHWC batch (device or pinned host) into the static input buffers."""
+    self.in_u8.copy_(images_u8, non_blocking=True)
+    if labels is not None:
+      self.labels.copy_(labels, non_blocking=True)
+
+  # --------------------------------------------------------------- forward
+  def _forward(self, training):
+    K = ops.K
+    K.decode_normalize(self.in_u8, self.xp, igemm.STEM_PAD, self.mean, self.std)
+    self.p_stem.run()
+    self.stem_bn.forward(self.stem_raw, self.stem_act, None, 1, training)
+    K.maxpool_fwd(self.stem_act, self.pool, self.pool_idx, 3, 2, 1)
+    for b in self.blocks:
+      for u, raw, act in ((b.u1, b.r1, b.a1), (b.u2, b.r2, b.a2)):
+        u.conv.forward()
+        u.bn.forward(raw, act, None, 1, training)
+      b.u3.conv.forward()
+      if b.ds is not None:
+        b.ds.conv.forward()
+        b.ds.bn.forward(b.rd, b.idn, None, 0, training)
+        idn = b.idn
+      else:
+        idn = b.x
+      b.u3.bn.forward(b.r3, b.out, idn, 1, training)
+    K.avgpool_fwd(self.last, self.avg)
+    self.fc.forward()
+
+  def _loss(self, with_grad):
+    self.loss_sum.zero_()
+    self.correct.zero_()
+    ops.K.softmax_xent(self.logits, self.labels, self.dlogits if with_grad else None,
+                       self.loss_sum, self.correct, self.num_classes, 1.0 / self.B)
+
+  # -------------------------------------------------------------- backward
+  def _backward(self):
+    K = ops.K
+    self.optim.zero_grads()
+    self.fc.backward()
+    K.avgpool_bwd(self.g_avg, self.g_last)
+    for b in reversed(self.blocks):
+      # out = relu(bn3(r3) + idn): masked gradient goes to both branches
+      b.u3.bn.backward(b.g_out, b.r3, b.out, b.g_r3, dres=b.g_out, relu=True)
+      b.u3.conv.backward()
+      b.u2.bn.backward(b.g_a2, b.r2, b.a2, b.g_r2, relu=True)
+      b.u2.conv.backward()
+      b.u1.bn.backward(b.g_a1, b.r1, b.a1, b.g_r1, relu=True)
+      b.u1.conv.backward()  # writes (ds) or accumulates (identity) into g_x
+      if b.ds is not None:
+        b.ds.bn.backward(b.g_out, b.rd, None, b.g_rd, relu=False)
+        b.ds.conv.backward()  # accumulates into g_x
+    K.maxpool_bwd(self.g_pool, self.pool_idx, self.g_stem_act, 3, 2, 1)
+    self.stem_bn.backward(self.g_stem_act, self.stem_raw, self.stem_act, self.g_stem_raw,
+                          relu=True)
+    self.p_stem_wgrad.run()
+
+  # ------------------------------------------------------------------ API
+  def step_kernels(self):
+    """Forward + loss + backward + optimizer on the static buffers (capturable)."""
+    self._forward(True)
+    self._loss(True)
+    self._backward()
+    self.optim.step()
+
+  def capture(self):
+    """Capture one training step into a CUDA graph (launch-bound inner loop -> one launch)."""
+    s = torch.cuda.Stream(device=self.device)
+    s.wait_stream(torch.cuda.current_stream(self.device))
+    with torch.cuda.stream(s):
+      for _ in range(2):
+        self.step_kernels()
+    torch.cuda.current_stream(self.device).wait_stream(s)
+    torch.cuda.synchronize(self.device)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+      self.step_kernels()
+    self.graph = g
+    return g
+
+  def train_step(self, images_u8=None, labels=None):
+    if images_u8 is not None:
+      self.set_input(images_u8, labels)
+    if self.graph is not None:
+      self.graph.replay()
+    else:
+      self.step_kernels()
+    return self.loss_sum  # device scalar: mean loss of the step
+
+  def forward_only(self, images_u8=None):
+    if images_u8 is not None:
+      self.set_input(images_u8)
+    self._forward(False)
+    return self.logits
+
+  def set_lr(self, lr):
+    self.optim.set_lr(lr)
+
+
+def piecewise_lr(epoch, batch_size, base=0.1, boundaries=(91, 136, 182), factors=(0.1, 0.01, 0.001)):
+  """LR schedule of the reference ResNet example (resnet_cifar_dist.py:35-66):
+  0.1 * bs/128, multiplied by 0.1 / 0.01 / 0.001 from epochs 91 / 136 / 182."""
+  lr = base * batch_size / 128.0
+  for b, f in zip(boundaries, factors):
+    if epoch >= b:
+      lr = base * batch_size / 128.0 * f
+  return lr

@@ -1,0 +1,431 @@
+"""Numerics checks of every native kernel against plain PyTorch fp32 references.
+
+Usage:  python tools/gpu_check.py            # run every check, each in its own subprocess
+        python tools/gpu_check.py NAME ...   # run the named checks in-process
+Each check runs under its own timeout so a misbehaving kernel cannot hang the box.
+Results are appended to gpurun_out/gpu_check.log.
+"""
+import os
+import subprocess
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+CHECKS = {}
+
+
+def check(fn):
+  CHECKS[fn.__name__] = fn
+  return fn
+
+
+def _rel(a, b):
+  import torch
+  a, b = a.float(), b.float()
+  return float((a - b).abs().max() / (b.abs().max() + 1e-6))
+
+
+def _report(name, err, tol):
+  ok = err == err and err < tol
+  print("CHECK {:34s} rel_err={:.3e} tol={:.1e} {}".format(name, err, tol, "OK" if ok else "FAIL"))
+  return ok
+
+
+def _conv_ref(x, w, stride, pad):
+  import torch
+  import torch.nn.functional as F
+  y = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), stride=stride,
+               padding=pad)
+  return y.permute(0, 2, 3, 1).contiguous()
+
+
+@check
+def gemm_nk():
+  import torch
+  from tensorflowonspark_b200.ops import igemm
+  ok = True
+  for (M, N, K) in [(256, 128, 64), (1024, 256, 512), (300, 200, 136), (4096, 1000, 2048),
+                    (128, 64, 5408)]:
+    a = torch.randn(M, K, device="cuda").bfloat16()
+    b = torch.randn(N, K, device="cuda").bfloat16()
+    bias = torch.randn(N, device="cuda")
+    out = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+    igemm.gemm(a, b, out, "nk", bias=bias, relu=True).run()
+    torch.cuda.synchronize()
+    ref = torch.relu(a.float() @ b.float().t() + bias)
+    ok &= _report("gemm_nk {}x{}x{}".format(M, N, K), _rel(out, ref), 2e-2)
+    out32 = torch.zeros(M, N, device="cuda", dtype=torch.float32)
+    igemm.gemm(a, b, out32, "nk").run()
+    torch.cuda.synchronize()
+    ok &= _report("gemm_nk fp32 {}x{}x{}".format(M, N, K), _rel(out32, a.float() @ b.float().t()),
+                  1e-3)
+  return ok
+
+
+@check
+def gemm_kn():
+  import torch
+  from tensorflowonspark_b200.ops import igemm
+  ok = True
+  for (M, N, K) in [(256, 128, 64), (512, 256, 1000), (384, 64, 256), (256, 2048, 1000)]:
+    a = torch.randn(M, K, device="cuda").bfloat16()
+    b = torch.randn(K, N, device="cuda").bfloat16()
+    out = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+    igemm.gemm(a, b, out, "kn").run()
+    torch.cuda.synchronize()
+    ok &= _report("gemm_kn {}x{}x{}".format(M, N, K), _rel(out, a.float() @ b.float()), 2e-2)
+  return ok
+
+
+@check
+def gemm_stats_accumulate():
+  import torch
+  from tensorflowonspark_b200.ops import igemm
+  M, N, K = 1000, 256, 128
+  a = torch.randn(M, K, device="cuda").bfloat16()
+  b = torch.randn(N, K, device="cuda").bfloat16()
+  out = torch.randn(M, N, device="cuda").bfloat16()
+  prev = out.clone()
+  s, ss = torch.zeros(N, device="cuda"), torch.zeros(N, device="cuda")
+  igemm.gemm(a, b, out, "nk", accumulate=True, stats=(s, ss)).run()
+  torch.cuda.synchronize()
+  ref = a.float() @ b.float().t() + prev.float()
+  ok = _report("gemm accumulate", _rel(out, ref), 2e-2)
+  ok &= _report("gemm fused col_sum", _rel(s, out.float().sum(0)), 1e-3)
+  ok &= _report("gemm fused col_sumsq", _rel(ss, (out.float() ** 2).sum(0)), 1e-3)
+  return ok
+
+
+@check
+def gemm_wgrad():
+  import torch
+  from tensorflowonspark_b200.ops import igemm
+  ok = True
+  for (M, Co, Ci) in [(1024, 128, 64), (4096, 256, 128), (2000, 1000, 2048), (512, 64, 64)]:
+    dy = torch.randn(M, Co, device="cuda").bfloat16()
+    x = torch.randn(M, Ci, device="cuda").bfloat16()
+    dw = torch.zeros(Co, Ci, device="cuda")
+    igemm.gemm_wgrad(dy, x, dw).run()
+    torch.cuda.synchronize()
+    ok &= _report("gemm_wgrad {}x{}x{}".format(M, Co, Ci), _rel(dw, dy.float().t() @ x.float()),
+                  1e-3)
+  return ok
+
+
+def _conv_case(N, H, W, Ci, Co, k, stride):
+  import torch
+  pad = k // 2
+  x = torch.randn(N, H, W, Ci, device="cuda").bfloat16()
+  w = (torch.randn(Co, k, k, Ci, device="cuda") * 0.1).bfloat16()
+  OH, OW = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+  return x, w, OH, OW, pad
+
+
+CONV_CASES = [(2, 16, 16, 64, 64, 3, 1), (4, 56, 56, 64, 128, 3, 1), (2, 14, 14, 256, 256, 3, 1),
+              (3, 7, 7, 128, 512, 3, 1), (2, 28, 28, 128, 128, 3, 2), (2, 56, 56, 256, 512, 1, 2),
+              (2, 15, 15, 64, 64, 3, 2), (2, 8, 8, 16, 24, 3, 1)]
+
+
+@check
+def conv_fprop():
+  import torch
+  from tensorflowonspark_b200.ops import igemm
+  ok = True
+  for case in CONV_CASES:
+    N, H, W, Ci, Co, k, stride = case
+    x, w, OH, OW, pad = _conv_case(*case)
+    y = torch.zeros(N, OH, OW, Co, device="cuda", dtype=torch.bfloat16)
+    s, ss = torch.zeros(Co, device="cuda"), torch.zeros(Co, device="cuda")
+    igemm.conv_fprop(x, w, y, stride, pad, stats=(s, ss)).run()
+    torch.cuda.synchronize()
+    ref = _conv_ref(x, w, stride, pad)
+    ok &= _report("fprop {}".format(case), _rel(y, ref), 2e-2)
+    ok &= _report("fprop stats {}".format(case), _rel(s, y.float().sum((0, 1, 2))), 2e-3)
+  return ok
+
+
+@check
+def conv_dgrad():
+  import torch
+  from tensorflowonspark_b200.ops import igemm
+  ok = True
+  for case in CONV_CASES:
+    N, H, W, Ci, Co, k, stride = case
+    x, w, OH, OW, pad = _conv_case(*case)
+    dy = torch.randn(N, OH, OW, Co, device="cuda").bfloat16()
+    xr = x.float().requires_grad_(True)
+    _conv_ref(xr, w, stride, pad).backward(dy.float())
+    base = torch.randn_like(x)
+    dx = base.clone()
+    igemm.conv_dgrad(dy, w, dx, stride, pad, accumulate=True).run()
+    torch.cuda.synchronize()
+    ok &= _report("dgrad+acc {}".format(case), _rel(dx, xr.grad + base.float()), 3e-2)
+    if not (k == 1 and stride == 2):
+      dx2 = torch.full_like(x, 7.0)
+      igemm.conv_dgrad(dy, w, dx2, stride, pad).run()
+      torch.cuda.synchronize()
+      ok &= _report("dgrad {}".format(case), _rel(dx2, xr.grad), 3e-2)
+  return ok
+
+
+@check
+def conv_wgrad():
+  import torch
+  from tensorflowonspark_b200.ops import igemm
+  ok = True
+  for case in CONV_CASES:
+    N, H, W, Ci, Co, k, stride = case
+    x, w, OH, OW, pad = _conv_case(*case)
+    dy = torch.randn(N, OH, OW, Co, device="cuda").bfloat16()
+    wr = w.float().requires_grad_(True)
+    _conv_ref(x, wr, stride, pad).backward(dy.float())
+    dw = torch.zeros(Co, k, k, Ci, device="cuda")
+    igemm.conv_wgrad(dy, x, dw, stride, pad).run()
+    torch.cuda.synchronize()
+    ok &= _report("wgrad {}".format(case), _rel(dw, wr.grad), 2e-3)
+  return ok
+
+
+@check
+def stem():
+  import torch
+  import torch.nn.functional as F
+  from tensorflowonspark_b200 import ops
+  from tensorflowonspark_b200.ops import igemm
+  ok = True
+  for (N, HW) in [(2, 64), (2, 224)]:
+    img = torch.randint(0, 256, (N, HW, HW, 3), device="cuda", dtype=torch.uint8)
+    OH, OW, Wp = igemm.stem_geometry(HW, HW)
+    xp = torch.zeros(N, HW, Wp, 8, device="cuda", dtype=torch.bfloat16)
+    mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+    ops.K.decode_normalize(img, xp, igemm.STEM_PAD, mean, std)
+    xn = (img.float() / 255 - torch.tensor(mean, device="cuda")) / torch.tensor(std, device="cuda")
+    ok &= _report("decode_normalize", _rel(xp[:, :, 3:3 + HW, :3], xn), 1e-2)
+    w = (torch.randn(64, 7, 7, 3, device="cuda") * 0.1).bfloat16()
+    wp = igemm.pack_stem_weight(w)
+    y = torch.zeros(N, OH, OW, 64, device="cuda", dtype=torch.bfloat16)
+    igemm.stem_fprop(xp, wp, y).run()
+    torch.cuda.synchronize()
+    xin = xp[:, :, 3:3 + HW, :3].float()
+    ref = _conv_ref(xin, w, 2, 3)
+    ok &= _report("stem fprop {}".format(HW), _rel(y, ref), 2e-2)
+    dy = torch.randn(N, OH, OW, 64, device="cuda").bfloat16()
+    wr = w.float().requires_grad_(True)
+    _conv_ref(xin, wr, 2, 3).backward(dy.float())
+    dwp = torch.zeros(64, 7, 64, device="cuda")
+    igemm.stem_wgrad(dy, xp, dwp).run()
+    torch.cuda.synchronize()
+    ok &= _report("stem wgrad {}".format(HW), _rel(igemm.unpack_stem_weight(dwp), wr.grad), 2e-3)
+  return ok
+
+
+@check
+def batchnorm():
+  import torch
+  from tensorflowonspark_b200 import ops
+  K = ops.K
+  ok = True
+  for (P, C) in [(4096, 64), (3000, 256), (1568, 2048), (1000, 24)]:
+    x = (torch.randn(P, C, device="cuda") * 2 + 1).bfloat16()
+    res = torch.randn(P, C, device="cuda").bfloat16()
+    gamma, beta = torch.rand(C, device="cuda") + 0.5, torch.randn(C, device="cuda")
+    z = lambda: torch.zeros(C, device="cuda")  # noqa: E731
+    s, ss, mean, invstd, scale, shift, rm, rv = z(), z(), z(), z(), z(), z(), z(), z() + 1
+    K.bn_stats(x, s, ss)
+    K.bn_finalize(s, ss, gamma, beta, rm, rv, mean, invstd, scale, shift, float(P), 1e-5, 0.1)
+    y = torch.empty_like(x)
+    K.bn_apply(x, res, scale, shift, y, 1)
+    torch.cuda.synchronize()
+    xf = x.float().requires_grad_(True)
+    g32, b32 = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    m, v = xf.mean(0), xf.var(0, unbiased=False)
+    yr = torch.relu((xf - m) / torch.sqrt(v + 1e-5) * g32 + b32 + res.float())
+    ok &= _report("bn mean P{} C{}".format(P, C), _rel(mean, m), 1e-3)
+    ok &= _report("bn fwd+res+relu", _rel(y, yr), 2e-2)
+    ok &= _report("bn sums cleared", float(s.abs().max() + ss.abs().max()), 1e-12)
+    dy = torch.randn(P, C, device="cuda").bfloat16()
+    yr.backward(dy.float())
+    dgamma, dbeta = z(), z()
+    dx, dres = torch.empty_like(x), torch.empty_like(x)
+    K.bn_bwd_reduce(dy, x, y, mean, invstd, dgamma, dbeta, True)
+    K.bn_bwd_apply(dy, x, y, gamma, mean, invstd, dgamma, dbeta, dx, dres, True)
+    torch.cuda.synchronize()
+    ok &= _report("bn dgamma", _rel(dgamma, g32.grad), 2e-2)
+    ok &= _report("bn dbeta", _rel(dbeta, b32.grad), 2e-2)
+    ok &= _report("bn dx", _rel(dx, xf.grad), 3e-2)
+    mask = (yr > 0).float()
+    ok &= _report("bn dres", _rel(dres, dy.float() * mask), 2e-2)
+  return ok
+
+
+@check
+def pools_loss():
+  import torch
+  import torch.nn.functional as F
+  from tensorflowonspark_b200 import ops
+  K = ops.K
+  ok = True
+  N, H, W, C = 3, 17, 17, 64
+  x = torch.randn(N, H, W, C, device="cuda").bfloat16()
+  OH = (H + 2 - 3) // 2 + 1
+  y = torch.empty(N, OH, OH, C, device="cuda", dtype=torch.bfloat16)
+  idx = torch.empty(N, OH, OH, C, device="cuda", dtype=torch.uint8)
+  K.maxpool_fwd(x, y, idx, 3, 2, 1)
+  xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+  yr = F.max_pool2d(xr, 3, 2, 1)
+  ok &= _report("maxpool fwd", _rel(y, yr.permute(0, 2, 3, 1)), 1e-6)
+  dy = torch.randn_like(y)
+  yr.backward(dy.float().permute(0, 3, 1, 2))
+  dx = torch.empty_like(x)
+  K.maxpool_bwd(dy, idx, dx, 3, 2, 1)
+  ok &= _report("maxpool bwd", _rel(dx, xr.grad.permute(0, 2, 3, 1)), 1e-2)
+  x = torch.randn(4, 7, 7, 256, device="cuda").bfloat16()
+  a = torch.empty(4, 256, device="cuda", dtype=torch.bfloat16)
+  K.avgpool_fwd(x, a)
+  ok &= _report("avgpool fwd", _rel(a, x.float().mean((1, 2))), 1e-2)
+  g = torch.randn(4, 256, device="cuda").bfloat16()
+  dx = torch.empty_like(x)
+  K.avgpool_bwd(g, dx)
+  ok &= _report("avgpool bwd", _rel(dx, (g.float() / 49)[:, None, None, :].expand_as(x)), 1e-2)
+  B, V = 64, 1000
+  logits = torch.randn(B, V, device="cuda") * 3
+  labels = torch.randint(0, V, (B,), device="cuda", dtype=torch.int32)
+  dl = torch.empty(B, V, device="cuda", dtype=torch.bfloat16)
+  loss, corr = torch.zeros(1, device="cuda"), torch.zeros(1, device="cuda")
+  K.softmax_xent(logits, labels, dl, loss, corr, V, 1.0 / B)
+  lr = logits.clone().requires_grad_(True)
+  lref = F.cross_entropy(lr, labels.long())
+  lref.backward()
+  ok &= _report("xent loss", _rel(loss, lref.detach().view(1)), 1e-4)
+  ok &= _report("xent dlogits", _rel(dl, lr.grad), 1e-2)
+  ok &= _report("xent correct", abs(float(corr) - float((logits.argmax(1) == labels).sum())), 0.5)
+  return ok
+
+
+@check
+def optimizer():
+  import torch
+  from tensorflowonspark_b200 import ops
+  ok = True
+  n = 100000 + 8
+  n = n // 8 * 8
+  for opt, name in ((0, "sgd"), (1, "momentum"), (2, "adam")):
+    w = torch.randn(n, device="cuda")
+    g = torch.randn(n, device="cuda")
+    s1, s2 = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    wb = torch.zeros(n, device="cuda", dtype=torch.bfloat16)
+    aux = torch.zeros(n - 50000, device="cuda")
+    hyper = torch.tensor([0.1, 0.9, 1e-2, 1.0, 0.9, 0.999, 1e-7, 1.0], device="cuda")
+    w0 = w.clone()
+    d = {"master": w.data_ptr(), "state1": s1.data_ptr(), "state2": s2.data_ptr(),
+         "hyper": hyper.data_ptr(), "begin": 0, "end": n, "decay_end": 50000, "world": 1,
+         "rank": 0, "slot": 0, "opt": opt, "grid": 64, "grads": [g.data_ptr()],
+         "weights": [wb.data_ptr()], "aux32": [aux.data_ptr()], "aux_begin": 50000}
+    ops.K.allreduce_opt(d)
+    torch.cuda.synchronize()
+    ge = g.clone()
+    ge[:50000] += 1e-2 * w0[:50000]
+    if opt == 0:
+      ref = w0 - 0.1 * ge
+    elif opt == 1:
+      ref = w0 - 0.1 * ge
+    else:
+      m = 0.1 * ge
+      v = 0.001 * ge * ge
+      ref = w0 - 0.1 * (m / 0.1) / (torch.sqrt(v / 0.001) + 1e-7)
+    ok &= _report("opt {} master".format(name), _rel(w, ref), 1e-4)
+    ok &= _report("opt {} bf16".format(name), _rel(wb, ref), 1e-2)
+    ok &= _report("opt {} aux32".format(name), _rel(aux, ref[50000:]), 1e-4)
+  return ok
+
+
+@check
+def mnist_small():
+  import torch
+  import torch.nn.functional as F
+  from tensorflowonspark_b200 import ops
+  K = ops.K
+  N, Co = 8, 32
+  x = torch.rand(N, 28, 28, device="cuda").bfloat16()
+  w = (torch.randn(Co, 9, device="cuda") * 0.3).bfloat16()
+  b = torch.randn(Co, device="cuda")
+  y = torch.empty(N, 26, 26, Co, device="cuda", dtype=torch.bfloat16)
+  K.conv3x3_c1_fwd(x, w, b, y, True)
+  ref = torch.relu(F.conv2d(x.float()[:, None], w.float().view(Co, 1, 3, 3), b)).permute(0, 2, 3, 1)
+  ok = _report("conv3x3_c1 fwd", _rel(y, ref), 2e-2)
+  dy = torch.randn_like(y)
+  dw, db = torch.zeros(Co, 9, device="cuda"), torch.zeros(Co, device="cuda")
+  K.conv3x3_c1_wgrad(x, dy, dw, db)
+  wr = w.float().view(Co, 1, 3, 3).requires_grad_(True)
+  F.conv2d(x.float()[:, None], wr).backward(dy.float().permute(0, 3, 1, 2))
+  ok &= _report("conv3x3_c1 wgrad", _rel(dw, wr.grad.view(Co, 9)), 1e-3)
+  ok &= _report("conv3x3_c1 dbias", _rel(db, dy.float().sum((0, 1, 2))), 1e-3)
+  xd = torch.randn(2, 9, 9, 32, device="cuda").bfloat16()
+  wd = torch.randn(9, 32, device="cuda").bfloat16()
+  for s in (1, 2):
+    OH = (9 - 1) // s + 1
+    yd = torch.empty(2, OH, OH, 32, device="cuda", dtype=torch.bfloat16)
+    K.depthwise3x3_fwd(xd, wd, yd, s)
+    refd = F.conv2d(xd.float().permute(0, 3, 1, 2), wd.float().t().reshape(32, 1, 3, 3), stride=s,
+                    padding=1, groups=32).permute(0, 2, 3, 1)
+    ok &= _report("depthwise3x3 s{}".format(s), _rel(yd, refd), 2e-2)
+  return ok
+
+
+@check
+def resnet_step():
+  import torch
+  from tensorflowonspark_b200.models import resnet
+  net = resnet.ResNetTrainer(depth=50, batch=8, image=64, num_classes=1000, lr=0.05)
+  x, y = net.synthetic_batch()
+  losses = []
+  for i in range(12):
+    net.train_step(x, y)
+    losses.append(float(net.loss_sum))
+  print("resnet50 b8 64px losses:", " ".join("%.3f" % l for l in losses))
+  ok = all(l == l for l in losses) and losses[-1] < losses[0]
+  print("CHECK resnet_step overfit {} -> {} {}".format(losses[0], losses[-1], "OK" if ok else "FAIL"))
+  return ok
+
+
+def main():
+  names = sys.argv[1:]
+  if names:
+    import torch
+    torch.manual_seed(0)
+    ok = True
+    for n in names:
+      try:
+        ok &= bool(CHECKS[n]())
+      except Exception as e:
+        import traceback
+        traceback.print_exc()
+        print("CHECK {} raised {}".format(n, e))
+        ok = False
+    sys.exit(0 if ok else 1)
+  os.makedirs("gpurun_out", exist_ok=True)
+  summary = []
+  with open("gpurun_out/gpu_check.log", "a") as log:
+    for n in CHECKS:
+      t0 = time.time()
+      try:
+        p = subprocess.run([sys.executable, __file__, n], capture_output=True, text=True,
+                           timeout=int(os.environ.get("TFOS_CHECK_TIMEOUT", "240")))
+        out, rc = p.stdout + p.stderr[-3000:], p.returncode
+      except subprocess.TimeoutExpired as e:
+        out, rc = "TIMEOUT\n" + str(e.stdout or "")[-2000:], 124
+      log.write("==== {} rc={} {:.1f}s\n{}\n".format(n, rc, time.time() - t0, out))
+      log.flush()
+      fails = [l for l in out.splitlines() if "FAIL" in l or "raised" in l or "Error" in l]
+      summary.append((n, rc, fails[:6]))
+      print("== {} rc={} ({:.1f}s)".format(n, rc, time.time() - t0))
+      for l in fails[:6]:
+        print("   ", l)
+  bad = [s for s in summary if s[1] != 0]
+  print("SUMMARY: {}/{} checks passed".format(len(summary) - len(bad), len(summary)))
+  sys.exit(1 if bad else 0)
+
+
+if __name__ == "__main__":
+  main()
