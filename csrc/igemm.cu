@@ -1,4 +1,6 @@
-// tcgen05 / TMEM / TMA implicit-GEMM kernels for sm_100a.
+// tcgen05 / TMEM / TMA implicit-GEMM kernels for sm_100a: the "forward-like" kernel
+// (fprop, dgrad, transposed conv, dense GEMM) and the host-side plan code.  The
+// weight-gradient kernel lives in igemm_wgrad.cu.
 //
 // Replaces what the reference reaches through TensorFlow -> cuDNN/cuBLAS for
 // its example models (conv fprop/dgrad/wgrad, dense
@@ -6,12 +8,18 @@
 // examples/resnet/resnet_cifar_dist.py:208, examples/segmentation/
 // segmentation_spark.py:67-119).
 //
-// Structure (both kernels): 192 threads = 6 warps, one CTA per SM, persistent
-// over a static round-robin tile list.
+// Structure: 320 threads = 10 warps, one CTA per SM, persistent over a static
+// round-robin tile list.
 //   warp 0   : TMA producer  (one lane issues cp.async.bulk.tensor into a smem ring)
 //   warp 1   : TMEM allocator + MMA issuer (one lane issues tcgen05.mma; the
 //              accumulator lives in TMEM, double-buffered across tiles)
-//   warps 2-5: epilogue (tcgen05.ld -> registers -> bias/ReLU/stats -> global)
+//   warps 2-9: epilogue.  Two warps share each TMEM lane quarter and split the
+//              64-column slabs between them (two warps per scheduler: the epilogue
+//              is instruction-latency bound with one).  tcgen05.ld -> bias / ReLU /
+//              bf16 rounding -> XOR-swizzled smem slab -> (a) per-column sum and
+//              sum of squares for the fused batch-norm statistics, read back
+//              column-wise, (b) coalesced global stores, 4 rows x 128 B per warp
+//              instruction, with optional read-modify-write accumulation.
 // Pipelines: smem full/empty mbarriers between TMA and MMA; TMEM full/empty
 // mbarriers between MMA and epilogue, so the epilogue of tile i overlaps the
 // main loop of tile i+1.
@@ -25,9 +33,13 @@
 
 namespace tfos {
 
+cudaError_t igemm_run_wgrad(const IGemmPlan* p, cudaStream_t s);  // igemm_wgrad.cu
+
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kBlockM = 128;
 constexpr int kABytes = kBlockM * 128;  // 128 rows x 64 bf16
 
@@ -37,20 +49,24 @@ struct FwdCfg {
   static constexpr int kStage = kABytes + kBBytes;
   static constexpr int kStages = (BN <= 64) ? 8 : (BN <= 128 ? 6 : 4);
   static constexpr int kTmemCols = 2 * BN;  // double-buffered fp32 accumulator
-  static constexpr int kStatBytes = 4 * BN * 2 * 4;
-  static constexpr int kSmem = kStages * kStage + kStatBytes + 256 + 1024;
+  static constexpr int kStatBytes = BN * 2 * 4;
+  static constexpr int kOutStageBytes = kEpiWarps * 4096;  // per warp: 32 rows x 128 B
+  static constexpr int kSmem = kStages * kStage + kStatBytes + kOutStageBytes + 256;
 };
+
+__device__ __forceinline__ void red_shared_add(float* p, float v) {
+  asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(smem_u32(p)), "f"(v) : "memory");
+}
 
 template <int BN, bool B_MN>
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const FwdArgs a, const int total_tiles) {
   using Cfg = FwdCfg<BN>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
   float* stat_smem = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStage);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStage + Cfg::kStatBytes);
+  uint8_t* out_stage = smem + Cfg::kStages * Cfg::kStage + Cfg::kStatBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + Cfg::kOutStageBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + Cfg::kStages;
   uint64_t* tfull = bars + 2 * Cfg::kStages;
@@ -61,6 +77,10 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) {  // SWIZZLE_128B operands need 1024-byte alignment
+      printf("tfos: dynamic shared memory is not 1024-byte aligned\n");
+      __trap();
+    }
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < Cfg::kStages; ++i) {
@@ -69,7 +89,7 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
+      mbar_init(&tempty[i], kEpiWarps);
     }
     fence_mbar_init();
   }
@@ -77,6 +97,8 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tmem_alloc(tmem_slot, Cfg::kTmemCols);
     tmem_relinquish();
   }
+  if (threadIdx.x >= 64)
+    for (int i = threadIdx.x - 64; i < BN * 2; i += kEpiThreads) stat_smem[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -159,10 +181,12 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     // ---------------------------------------------------------------- epilogue
-    const int q = warp & 3;  // TMEM lane quarter this warp may read
-    const int ew = warp - 2;
-    const int et = threadIdx.x - 64;  // 0..127
+    const int ew = warp - 2;    // 0..7
+    const int q = warp & 3;     // TMEM lane quarter this warp may read
+    const int half = ew >> 2;   // which column slabs / chunks this warp takes
+    const int et = threadIdx.x - 64;
     const bool do_stats = a.col_sum != nullptr;
+    const uint32_t stg = smem_u32(out_stage + ew * 4096);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -181,317 +205,201 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const long long pix =
           (static_cast<long long>(n) * a.OH + (h * a.osh + a.ooh)) * a.OW + (w * a.osw + a.oow);
       const long long off = pix * a.ldo + static_cast<long long>(nt) * BN;
+      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
 
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
+      const bool fast = !a.out_fp32 && (nt * BN + BN <= a.n_valid) && (a.ldo & 7) == 0;
+      if (fast) {
+        __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(a.out);
+        const bool relu_early = a.relu && !a.accumulate;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c * 32, v);
-        tmem_ld_wait();
-        const int col0 = nt * BN + c * 32;
-        float f[32];
+        for (int c = half; c < BN / 64; c += 2) {
+          uint32_t v[64];
+          {
+            uint32_t (&lo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
+            uint32_t (&hi)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[32]);
+            tmem_ld_32x32(tbase + c * 64, lo);
+            tmem_ld_32x32(tbase + c * 64 + 32, hi);
+            tmem_ld_wait();
+          }
+          const int col0 = nt * BN + c * 64;
+          uint32_t pk[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (a.bias != nullptr) {
+          for (int j = 0; j < 64; j += 2) {
+            float f0 = __uint_as_float(v[j]), f1 = __uint_as_float(v[j + 1]);
+            if (a.bias != nullptr) {
+              f0 += __ldg(a.bias + col0 + j);
+              f1 += __ldg(a.bias + col0 + j + 1);
+            }
+            if (relu_early) {
+              f0 = fmaxf(f0, 0.f);
+              f1 = fmaxf(f1, 0.f);
+            }
+            pk[j >> 1] = (do_stats && !valid) ? 0u : pack_bf16x2(f0, f1);
+          }
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < a.n_valid) f[j] += __ldg(a.bias + col0 + j);
+          for (int sgm = 0; sgm < 8; ++sgm) {
+            const uint32_t addr = stg + lane * 128 + ((sgm ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[sgm * 4]),
+                         "r"(pk[sgm * 4 + 1]), "r"(pk[sgm * 4 + 2]), "r"(pk[sgm * 4 + 3])
+                         : "memory");
+          }
+          __syncwarp();
+          if (do_stats) {
+            // lane l owns columns (2l, 2l+1) of the slab: word (l & 3) of segment (l >> 2);
+            // all lanes read the same row -> 32 distinct banks.  Statistics are taken of the
+            // rounded values that are stored; rows outside the tensor were zeroed above.
+            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+              uint32_t wv;
+              const uint32_t addr = stg + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2));
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(wv) : "r"(addr));
+              const float2 xy = unpack_bf16x2(wv);
+              s0 += xy.x, s1 += xy.y;
+              q0 += xy.x * xy.x, q1 += xy.y * xy.y;
+            }
+            float* st = stat_smem + (c * 64 + 2 * lane) * 2;
+            red_shared_add(st + 0, s0);
+            red_shared_add(st + 1, q0);
+            red_shared_add(st + 2, s1);
+            red_shared_add(st + 3, q1);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r2 = i * 4 + (lane >> 3), sg2 = lane & 7;
+            uint4 val;
+            const uint32_t addr = stg + r2 * 128 + ((sg2 ^ (r2 & 7)) << 4);
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
+                         : "r"(addr));
+            const long long roff = __shfl_sync(0xffffffff, off, r2);
+            const int rvalid = __shfl_sync(0xffffffff, static_cast<int>(valid), r2);
+            if (rvalid) {
+              __nv_bfloat16* o = obase + roff + c * 64 + sg2 * 8;
+              if (a.accumulate) {
+                const uint4 p = *reinterpret_cast<const uint4*>(o);
+                float2 n0 = unpack_bf16x2(val.x), n1 = unpack_bf16x2(val.y),
+                       n2 = unpack_bf16x2(val.z), n3 = unpack_bf16x2(val.w);
+                const float2 p0 = unpack_bf16x2(p.x), p1 = unpack_bf16x2(p.y),
+                             p2 = unpack_bf16x2(p.z), p3 = unpack_bf16x2(p.w);
+                n0.x += p0.x, n0.y += p0.y, n1.x += p1.x, n1.y += p1.y;
+                n2.x += p2.x, n2.y += p2.y, n3.x += p3.x, n3.y += p3.y;
+                if (a.relu) {
+                  n0.x = fmaxf(n0.x, 0.f), n0.y = fmaxf(n0.y, 0.f), n1.x = fmaxf(n1.x, 0.f);
+                  n1.y = fmaxf(n1.y, 0.f), n2.x = fmaxf(n2.x, 0.f), n2.y = fmaxf(n2.y, 0.f);
+                  n3.x = fmaxf(n3.x, 0.f), n3.y = fmaxf(n3.y, 0.f);
+                }
+                val.x = pack_bf16x2(n0.x, n0.y), val.y = pack_bf16x2(n1.x, n1.y);
+                val.z = pack_bf16x2(n2.x, n2.y), val.w = pack_bf16x2(n3.x, n3.y);
+              }
+              *reinterpret_cast<uint4*>(o) = val;
+            }
+          }
+          __syncwarp();
         }
-        if (a.out_fp32) {
-          float* o = reinterpret_cast<float*>(a.out) + off + c * 32;
-          if (valid) {
-            if (a.accumulate) {
+      } else {
+        // general path: fp32 output, ragged N, or unaligned pitch (dense heads, tails)
+#pragma unroll 1
+        for (int c = half; c < BN / 32; c += 2) {
+          uint32_t v[32];
+          tmem_ld_32x32(tbase + c * 32, v);
+          tmem_ld_wait();
+          const int col0 = nt * BN + c * 32;
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (a.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < a.n_valid) f[j] += __ldg(a.bias + col0 + j);
+          }
+          if (a.out_fp32) {
+            float* o = reinterpret_cast<float*>(a.out) + off + c * 32;
+            if (valid) {
+              if (a.accumulate) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (col0 + j < a.n_valid) f[j] += o[j];
+              }
+              if (a.relu) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+              }
+              if (col0 + 32 <= a.n_valid && (a.ldo & 3) == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                  *reinterpret_cast<float4*>(o + j) =
+                      make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (col0 + j < a.n_valid) o[j] = f[j];
+              }
+            }
+          } else {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) + off + c * 32;
+            if (valid && a.accumulate) {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (col0 + j < a.n_valid) f[j] += o[j];
+                if (col0 + j < a.n_valid) f[j] += __bfloat162float(o[j]);
             }
             if (a.relu) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
             }
-            if (col0 + 32 <= a.n_valid && (a.ldo & 3) == 0) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < a.n_valid) o[j] = f[j];
-            }
-          }
-        } else {
-          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) + off + c * 32;
-          const bool vec = col0 + 32 <= a.n_valid && (a.ldo & 7) == 0;
-          if (valid && a.accumulate) {
-            if (vec) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                const uint4 p = *reinterpret_cast<const uint4*>(o + j);
-                const float2 p0 = unpack_bf16x2(p.x), p1 = unpack_bf16x2(p.y),
-                             p2 = unpack_bf16x2(p.z), p3 = unpack_bf16x2(p.w);
-                f[j] += p0.x, f[j + 1] += p0.y, f[j + 2] += p1.x, f[j + 3] += p1.y;
-                f[j + 4] += p2.x, f[j + 5] += p2.y, f[j + 6] += p3.x, f[j + 7] += p3.y;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < a.n_valid) f[j] += __bfloat162float(o[j]);
-            }
-          }
-          if (a.relu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-          }
-          // Round once; statistics are taken of the values actually stored.
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __bfloat162float(__float2bfloat16_rn(f[j]));
-          if (valid) {
-            if (vec) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 p;
-                p.x = pack_bf16x2(f[j], f[j + 1]);
-                p.y = pack_bf16x2(f[j + 2], f[j + 3]);
-                p.z = pack_bf16x2(f[j + 4], f[j + 5]);
-                p.w = pack_bf16x2(f[j + 6], f[j + 7]);
-                *reinterpret_cast<uint4*>(o + j) = p;
-              }
-            } else {
+            for (int j = 0; j < 32; ++j) f[j] = __bfloat162float(__float2bfloat16_rn(f[j]));
+            if (valid) {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
                 if (col0 + j < a.n_valid) o[j] = __float2bfloat16_rn(f[j]);
             }
           }
-        }
-        if (do_stats) {
-          // Column sums over the 32 rows of this warp by a transpose-reduce
-          // butterfly: after 5 steps lane j holds the totals of column j.
-          float s[32], ss[32];
+          if (do_stats) {
+            // transpose-reduce butterfly: after 5 steps lane j holds the totals of column j
+            float s[32], ss[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float x = valid ? f[j] : 0.f;
-            s[j] = x;
-            ss[j] = x * x;
-          }
-#pragma unroll
-          for (int step = 16; step >= 1; step >>= 1) {
-            const bool upper = (lane & step) != 0;
-#pragma unroll
-            for (int j = 0; j < step; ++j) {
-              const float send_s = upper ? s[j] : s[j + step];
-              const float send_q = upper ? ss[j] : ss[j + step];
-              const float recv_s = __shfl_xor_sync(0xffffffff, send_s, step);
-              const float recv_q = __shfl_xor_sync(0xffffffff, send_q, step);
-              s[j] = (upper ? s[j + step] : s[j]) + recv_s;
-              ss[j] = (upper ? ss[j + step] : ss[j]) + recv_q;
+            for (int j = 0; j < 32; ++j) {
+              const float x = valid ? f[j] : 0.f;
+              s[j] = x;
+              ss[j] = x * x;
             }
+#pragma unroll
+            for (int step = 16; step >= 1; step >>= 1) {
+              const bool upper = (lane & step) != 0;
+#pragma unroll
+              for (int j = 0; j < step; ++j) {
+                const float send_s = upper ? s[j] : s[j + step];
+                const float send_q = upper ? ss[j] : ss[j + step];
+                const float recv_s = __shfl_xor_sync(0xffffffff, send_s, step);
+                const float recv_q = __shfl_xor_sync(0xffffffff, send_q, step);
+                s[j] = (upper ? s[j + step] : s[j]) + recv_s;
+                ss[j] = (upper ? ss[j + step] : ss[j]) + recv_q;
+              }
+            }
+            red_shared_add(stat_smem + (c * 32 + lane) * 2 + 0, s[0]);
+            red_shared_add(stat_smem + (c * 32 + lane) * 2 + 1, ss[0]);
           }
-          stat_smem[(ew * BN + c * 32 + lane) * 2 + 0] = s[0];
-          stat_smem[(ew * BN + c * 32 + lane) * 2 + 1] = ss[0];
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
       if (do_stats) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        for (int c = et; c < BN; c += 128) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int c = et; c < BN; c += kEpiThreads) {
           const int col = nt * BN + c;
           if (col < a.n_valid) {
-            float s = 0.f, ss = 0.f;
-#pragma unroll
-            for (int wq = 0; wq < 4; ++wq) {
-              s += stat_smem[(wq * BN + c) * 2 + 0];
-              ss += stat_smem[(wq * BN + c) * 2 + 1];
-            }
-            atomicAdd(a.col_sum + col, s);
-            atomicAdd(a.col_sumsq + col, ss);
+            atomicAdd(a.col_sum + col, stat_smem[c * 2 + 0]);
+            atomicAdd(a.col_sumsq + col, stat_smem[c * 2 + 1]);
           }
+          stat_smem[c * 2 + 0] = 0.f;
+          stat_smem[c * 2 + 1] = 0.f;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
-}
-
-// ------------------------------------------------------------------- wgrad
-// dW[m, tap, n] += sum_pixels dY[pixel, m] * X[pixel + tap, n].  Both operands
-// are MN-major in shared memory (the contiguous global dimension is channels,
-// the reduction runs over pixel rows), one TMA box of <=128 pixels per stage.
-template <int BN>
-struct WgCfg {
-  static constexpr int kAStage = 2 * 128 * 128;          // two 64-channel boxes, <=128 pixels
-  static constexpr int kBStage = (BN / 64) * 128 * 128;
-  static constexpr int kStage = kAStage + kBStage;
-  static constexpr int kStages = (BN <= 64) ? 4 : (BN <= 128 ? 3 : 2);
-  static constexpr int kTmemCols = 2 * BN;
-  static constexpr int kSmem = kStages * kStage + 256 + 1024;
-};
-
-template <int BN>
-__global__ void __launch_bounds__(kThreads, 1)
-igemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                   const WgradArgs a, const int total_work) {
-  using Cfg = WgCfg<BN>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStage);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + Cfg::kStages;
-  uint64_t* tfull = bars + 2 * Cfg::kStages;
-  uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-
-  const int warp = __shfl_sync(0xffffffff, threadIdx.x >> 5, 0);
-  const int lane = threadIdx.x & 31;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-    for (int i = 0; i < Cfg::kStages; ++i) {
-      mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
-    }
-    fence_mbar_init();
-  }
-  if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  const int total_boxes = a.tiles_w * a.tiles_h * a.tiles_n;
-  const int boxes_per_split = (total_boxes + a.k_splits - 1) / a.k_splits;
-  const uint32_t box_bytes = static_cast<uint32_t>(a.box_rows) * 128u;
-  const uint32_t stage_tx = box_bytes * (2 + BN / 64);
-
-  // work item -> (tap, m tile, n tile, k split); splits vary fastest so that
-  // concurrently running CTAs stream disjoint pixels of the same tile.
-  auto decode = [&](int work, int& t, int& mt, int& nt, int& b0, int& b1) {
-    const int ks = work % a.k_splits;
-    int r = work / a.k_splits;
-    nt = r % a.n_tiles;
-    r /= a.n_tiles;
-    mt = r % a.m_tiles;
-    t = r / a.m_tiles;
-    b0 = ks * boxes_per_split;
-    b1 = min(b0 + boxes_per_split, total_boxes);
-  };
-
-  if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
-        int t, mt, nt, b0, b1;
-        decode(work, t, mt, nt, b0, b1);
-        for (int b = b0; b < b1; ++b) {
-          const int tw = b % a.tiles_w;
-          const int th = (b / a.tiles_w) % a.tiles_h;
-          const int tn = b / (a.tiles_w * a.tiles_h);
-          const int pw = tw * a.box_w, ph = th * a.box_h, pn = tn * a.box_n;
-          mbar_wait(&empty[stage], phase ^ 1);
-          uint8_t* sA = smem + stage * Cfg::kStage;
-          uint8_t* sB = sA + Cfg::kAStage;
-          mbar_expect_tx(&full[stage], stage_tx);
-#pragma unroll
-          for (int j = 0; j < 2; ++j)
-            tma_load_4d(sA + j * box_bytes, &tmA, &full[stage], mt * 128 + j * 64, pw, ph, pn);
-#pragma unroll
-          for (int j = 0; j < BN / 64; ++j)
-            tma_load_4d(sB + j * box_bytes, &tmB, &full[stage], nt * BN + j * 64 + a.tap_dc[t],
-                        pw * a.mul_w + a.tap_dw[t], ph * a.mul_h + a.tap_dh[t], pn);
-          if (++stage == Cfg::kStages) {
-            stage = 0;
-            phase ^= 1;
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BN, true, true);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      const int mmas = a.box_rows / 16;
-      for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
-        int t, mt, nt, b0, b1;
-        decode(work, t, mt, nt, b0, b1);
-        mbar_wait(&tempty[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int b = b0; b < b1; ++b) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint32_t a_base = smem_u32(smem + stage * Cfg::kStage);
-          const uint32_t b_base = a_base + Cfg::kAStage;
-          for (int k = 0; k < mmas; ++k) {
-            const uint64_t adesc = umma_desc_sw128(a_base + k * 2048, box_bytes, 1024);
-            const uint64_t bdesc = umma_desc_sw128(b_base + k * 2048, box_bytes, 1024);
-            umma_bf16(d_tmem, adesc, bdesc, idesc, (b > b0 || k > 0) ? 1u : 0u);
-          }
-          umma_commit(&empty[stage]);
-          if (++stage == Cfg::kStages) {
-            stage = 0;
-            phase ^= 1;
-          }
-        }
-        umma_commit(&tfull[acc]);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
-      }
-    }
-  } else {
-    const int q = warp & 3;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
-      int t, mt, nt, b0, b1;
-      decode(work, t, mt, nt, b0, b1);
-      const int m = mt * 128 + q * 32 + lane;
-      const bool valid = m < a.m_valid && b1 > b0;
-      float* o = a.dw + static_cast<long long>(m) * a.ldw + a.tap_out[t] + nt * BN;
-      mbar_wait(&tfull[acc], acc_phase);
-      tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c * 32, v);
-        tmem_ld_wait();
-        const int col0 = nt * BN + c * 32;
-        if (valid) {
-          if (col0 + 32 <= a.n_valid && (a.ldw & 3) == 0 && (a.tap_out[t] & 3) == 0) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              red_add_f32x4(o + c * 32 + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                            __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < a.n_valid) atomicAdd(o + c * 32 + j, __uint_as_float(v[j]));
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -553,34 +461,18 @@ bool encode(const TmapDesc& d, CUtensorMap* out, char* err, int errlen) {
   return true;
 }
 
-template <typename K>
-cudaError_t set_smem(K kernel, int bytes) {
-  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-}
-
 template <int BN, bool B_MN>
 cudaError_t launch_fwd(const IGemmPlan* p, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = set_smem(igemm_fwd_kernel<BN, B_MN>, FwdCfg<BN>::kSmem);
+    cudaError_t e = cudaFuncSetAttribute(igemm_fwd_kernel<BN, B_MN>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         FwdCfg<BN>::kSmem);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   igemm_fwd_kernel<BN, B_MN><<<p->grid, kThreads, FwdCfg<BN>::kSmem, s>>>(p->tmA, p->tmB, p->fa,
                                                                            p->total_work);
-  return cudaGetLastError();
-}
-
-template <int BN>
-cudaError_t launch_wgrad(const IGemmPlan* p, cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = set_smem(igemm_wgrad_kernel<BN>, WgCfg<BN>::kSmem);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
-  igemm_wgrad_kernel<BN><<<p->grid, kThreads, WgCfg<BN>::kSmem, s>>>(p->tmA, p->tmB, p->wa,
-                                                                    p->total_work);
   return cudaGetLastError();
 }
 
@@ -595,6 +487,10 @@ IGemmPlan* igemm_plan_fwd(const TmapDesc& a, const TmapDesc& b, const FwdArgs& a
   const int rows = args.box_w * args.box_h * args.box_n;
   if (rows < 1 || rows > 128 || args.num_taps < 1 || args.num_taps > kMaxTaps) {
     snprintf(err, errlen, "bad box rows %d or taps %d", rows, args.num_taps);
+    return nullptr;
+  }
+  if (args.col_sum != nullptr && args.accumulate) {
+    snprintf(err, errlen, "fused statistics cannot be combined with accumulate");
     return nullptr;
   }
   IGemmPlan* p = new (std::nothrow) IGemmPlan();
@@ -640,24 +536,18 @@ IGemmPlan* igemm_plan_wgrad(const TmapDesc& a, const TmapDesc& b, const WgradArg
 }
 
 cudaError_t igemm_run(const IGemmPlan* p, cudaStream_t s) {
-  if (p->kind == 0) {
-    if (p->b_mn) {
-      switch (p->bn) {
-        case 64: return launch_fwd<64, true>(p, s);
-        case 128: return launch_fwd<128, true>(p, s);
-        default: return launch_fwd<256, true>(p, s);
-      }
-    }
+  if (p->kind == 1) return igemm_run_wgrad(p, s);
+  if (p->b_mn) {
     switch (p->bn) {
-      case 64: return launch_fwd<64, false>(p, s);
-      case 128: return launch_fwd<128, false>(p, s);
-      default: return launch_fwd<256, false>(p, s);
+      case 64: return launch_fwd<64, true>(p, s);
+      case 128: return launch_fwd<128, true>(p, s);
+      default: return launch_fwd<256, true>(p, s);
     }
   }
   switch (p->bn) {
-    case 64: return launch_wgrad<64>(p, s);
-    case 128: return launch_wgrad<128>(p, s);
-    default: return launch_wgrad<256>(p, s);
+    case 64: return launch_fwd<64, false>(p, s);
+    case 128: return launch_fwd<128, false>(p, s);
+    default: return launch_fwd<256, false>(p, s);
   }
 }
 

@@ -1,0 +1,223 @@
+// Weight-gradient tcgen05 kernel (split out of igemm.cu): dW[m, tap, n] += sum over pixels.
+// See igemm.cu for the structure shared by both kernels (TMA producer warp, single-thread
+// MMA issuer with TMEM accumulators, epilogue warps).
+#include <stdio.h>
+#include <string.h>
+
+#include "igemm.h"
+#include "ptx.cuh"
+
+namespace tfos {
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kBlockM = 128;
+
+// ------------------------------------------------------------------- wgrad
+// dW[m, tap, n] += sum_pixels dY[pixel, m] * X[pixel + tap, n].  Both operands
+// are MN-major in shared memory (the contiguous global dimension is channels,
+// the reduction runs over pixel rows), one TMA box of <=128 pixels per stage.
+template <int BN>
+struct WgCfg {
+  static constexpr int kAStage = 2 * 128 * 128;          // two 64-channel boxes, <=128 pixels
+  static constexpr int kBStage = (BN / 64) * 128 * 128;
+  static constexpr int kStage = kAStage + kBStage;
+  static constexpr int kStages = (BN <= 64) ? 4 : (BN <= 128 ? 3 : 2);
+  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kSmem = kStages * kStage + 256 + 1024;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+igemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const WgradArgs a, const int total_work) {
+  using Cfg = WgCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStage);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + Cfg::kStages;
+  uint64_t* tfull = bars + 2 * Cfg::kStages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = __shfl_sync(0xffffffff, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_boxes = a.tiles_w * a.tiles_h * a.tiles_n;
+  const int boxes_per_split = (total_boxes + a.k_splits - 1) / a.k_splits;
+  const uint32_t box_bytes = static_cast<uint32_t>(a.box_rows) * 128u;
+  const uint32_t stage_tx = box_bytes * (2 + BN / 64);
+
+  // work item -> (tap, m tile, n tile, k split); splits vary fastest so that
+  // concurrently running CTAs stream disjoint pixels of the same tile.
+  auto decode = [&](int work, int& t, int& mt, int& nt, int& b0, int& b1) {
+    const int ks = work % a.k_splits;
+    int r = work / a.k_splits;
+    nt = r % a.n_tiles;
+    r /= a.n_tiles;
+    mt = r % a.m_tiles;
+    t = r / a.m_tiles;
+    b0 = ks * boxes_per_split;
+    b1 = min(b0 + boxes_per_split, total_boxes);
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+        int t, mt, nt, b0, b1;
+        decode(work, t, mt, nt, b0, b1);
+        for (int b = b0; b < b1; ++b) {
+          const int tw = b % a.tiles_w;
+          const int th = (b / a.tiles_w) % a.tiles_h;
+          const int tn = b / (a.tiles_w * a.tiles_h);
+          const int pw = tw * a.box_w, ph = th * a.box_h, pn = tn * a.box_n;
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sA = smem + stage * Cfg::kStage;
+          uint8_t* sB = sA + Cfg::kAStage;
+          mbar_expect_tx(&full[stage], stage_tx);
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            tma_load_4d(sA + j * box_bytes, &tmA, &full[stage], mt * 128 + j * 64, pw, ph, pn);
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j)
+            tma_load_4d(sB + j * box_bytes, &tmB, &full[stage], nt * BN + j * 64 + a.tap_dc[t],
+                        pw * a.mul_w + a.tap_dw[t], ph * a.mul_h + a.tap_dh[t], pn);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BN, true, true);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      const int mmas = a.box_rows / 16;
+      for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+        int t, mt, nt, b0, b1;
+        decode(work, t, mt, nt, b0, b1);
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int b = b0; b < b1; ++b) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + stage * Cfg::kStage);
+          const uint32_t b_base = a_base + Cfg::kAStage;
+          for (int k = 0; k < mmas; ++k) {
+            const uint64_t adesc = umma_desc_sw128(a_base + k * 2048, box_bytes, 1024);
+            const uint64_t bdesc = umma_desc_sw128(b_base + k * 2048, box_bytes, 1024);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, (b > b0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+      int t, mt, nt, b0, b1;
+      decode(work, t, mt, nt, b0, b1);
+      const int m = mt * 128 + q * 32 + lane;
+      const bool valid = m < a.m_valid && b1 > b0;
+      float* o = a.dw + static_cast<long long>(m) * a.ldw + a.tap_out[t] + nt * BN;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c * 32, v);
+        tmem_ld_wait();
+        const int col0 = nt * BN + c * 32;
+        if (valid) {
+          if (col0 + 32 <= a.n_valid && (a.ldw & 3) == 0 && (a.tap_out[t] & 3) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              red_add_f32x4(o + c * 32 + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                            __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < a.n_valid) atomicAdd(o + c * 32 + j, __uint_as_float(v[j]));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+template <int BN>
+cudaError_t launch_wgrad(const IGemmPlan* p, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_wgrad_kernel<BN>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         WgCfg<BN>::kSmem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  igemm_wgrad_kernel<BN><<<p->grid, kThreads, WgCfg<BN>::kSmem, s>>>(p->tmA, p->tmB, p->wa,
+                                                                    p->total_work);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t igemm_run_wgrad(const IGemmPlan* p, cudaStream_t s) {
+  switch (p->bn) {
+    case 64: return launch_wgrad<64>(p, s);
+    case 128: return launch_wgrad<128>(p, s);
+    default: return launch_wgrad<256>(p, s);
+  }
+}
+
+}  // namespace tfos

@@ -1,0 +1,270 @@
+"""In-process helpers for the user's ``map_fun`` (reference: tensorflowonspark/TFNode.py).
+
+* :class:`DataFeed` - the consumer end of InputMode.SPARK (reference TFNode.py:234-342), same
+  ``next_batch / should_stop / batch_results / terminate`` contract, plus a device fast path
+  (``next_batch_tensors``) that moves ring blocks pinned-host -> GPU on a copy stream.
+* :func:`hdfs_path` - path normalisation against the cluster's default filesystem (:32-67).
+* :func:`start_cluster_server` - where the reference started a ``tf.train.Server`` (TF1 only,
+  :70-154), this returns a :class:`ClusterServer` handle: a NCCL/gloo process group for sync
+  data parallelism or a GPU-resident parameter server for the async path.
+* :func:`export_saved_model`, :func:`release_port`, and the deprecated module-level stubs.
+"""
+import getpass
+import logging
+import os
+import queue as _queue_mod
+
+from . import marker
+
+logger = logging.getLogger(__name__)
+
+#: schemes understood by Hadoop-compatible filesystems; paths carrying one are already absolute
+HADOOP_SCHEMES = ("adl://", "file://", "hdfs://", "oss://", "s3://", "s3a://", "s3n://", "swift://",
+                  "viewfs://", "wasb://")
+
+
+def hdfs_path(ctx, path):
+  """Absolute, scheme-qualified version of ``path`` for this cluster's default filesystem."""
+  if path.startswith(HADOOP_SCHEMES):
+    return path
+  fs = ctx.defaultFS
+  if path.startswith("/"):
+    return fs + path
+  if fs.startswith(("hdfs://", "viewfs://")):
+    return "{}/user/{}/{}".format(fs, getpass.getuser(), path)
+  if fs.startswith("file://"):
+    return "{}/{}/{}".format(fs, ctx.working_dir[1:], path)
+  logger.warning("Unknown scheme %s with relative path: %s", fs, path)
+  return "{}/{}".format(fs, path)
+
+
+def local_path(path):
+  """Strip a ``file://`` scheme so the path can be opened with ordinary file APIs."""
+  return path[len("file://"):] if path.startswith("file://") else path
+
+
+class ClusterServer(object):
+  """What :func:`start_cluster_server` hands back in place of a ``tf.train.Server``.
+
+  ``target`` names the rendezvous (``tcp://host:port``) the way ``server.target`` named the gRPC
+  endpoint; ``join()`` parks a ps node until the driver stops it, like ``server.join()``.
+  """
+
+  def __init__(self, ctx, group=None, ps=None):
+    self.ctx, self.group, self.ps = ctx, group, ps
+    self.target = "tcp://{}:{}".format(os.environ.get("MASTER_ADDR", "127.0.0.1"),
+                                       os.environ.get("MASTER_PORT", "0"))
+
+  def join(self):
+    if self.ps is not None:
+      self.ps.serve_forever()
+    else:
+      import time
+      while True:
+        time.sleep(3600)
+
+
+def start_cluster_server(ctx, num_gpus=1, rdma=False, backend=None, async_ps=None):
+  """Join this node to the cluster's communication substrate.
+
+  Returns ``(cluster_spec, server)`` like the reference.  With ``num_ps == 0`` every worker
+  enters a ``torch.distributed`` process group (NCCL when a GPU is visible, gloo otherwise);
+  when the cluster has ps nodes, ps processes host the parameters on their GPU and workers get
+  push/pull handles (parallel/ps.py).  ``rdma`` is accepted for signature compatibility: NVLink
+  peer access supersedes the reference's ``grpc+verbs`` switch (TFNode.py:129-130).
+  """
+  from .parallel import process_group
+  has_ps = bool(ctx.cluster_spec.get("ps"))
+  if async_ps is None:
+    async_ps = has_ps
+  if async_ps:
+    from .parallel import ps as ps_mod
+    handle = ps_mod.attach(ctx)
+    return ctx.cluster_spec, ClusterServer(ctx, ps=handle)
+  group = process_group.init_from_ctx(ctx, backend=backend)
+  return ctx.cluster_spec, ClusterServer(ctx, group=group)
+
+
+def export_saved_model(sess_or_model, export_dir, tag_set="serve", signatures=None):
+  """Write an inference artefact to ``export_dir`` (weights + a JSON signature).
+
+  The reference's version (TFNode.py:162-211) wrote a TF1 SavedModel from a session; here the
+  first argument is any object with ``state_dict()`` (a native-engine model or a torch module).
+  ``signatures`` maps signature keys to ``{'inputs': {alias: tensor_name}, 'outputs': {...}}``.
+  """
+  from .utils import checkpoint
+  return checkpoint.export_model(sess_or_model, export_dir, tag_set=tag_set, signatures=signatures)
+
+
+def release_port(ctx):
+  """Close the socket that has been holding this node's reserved port (reference :214-221)."""
+  if getattr(ctx, "tmp_socket", None) is not None:
+    logger.info("releasing reserved port %s", ctx.tmp_socket.getsockname())
+    ctx.tmp_socket.close()
+    ctx.tmp_socket = None
+  else:
+    logger.warning("release_port() called but no port is being held")
+
+
+def next_batch(mgr, batch_size, qname="input"):
+  """*DEPRECATED*: use :class:`DataFeed`."""
+  raise Exception("DEPRECATED: Use TFNode.DataFeed class instead")
+
+
+def batch_results(mgr, results, qname="output"):
+  """*DEPRECATED*: use :class:`DataFeed`."""
+  raise Exception("DEPRECATED: Use TFNode.DataFeed class instead")
+
+
+def terminate(mgr, qname="input"):
+  """*DEPRECATED*: use :class:`DataFeed`."""
+  raise Exception("DEPRECATED: Use TFNode.DataFeed class instead")
+
+
+def _value(proxy):
+  return proxy._getvalue() if hasattr(proxy, "_getvalue") else proxy
+
+
+class DataFeed(object):
+  """Consumer of the rows Spark feeds into this node.
+
+  Args:
+    mgr: this executor's TFManager.
+    train_mode: True when feeding training data (no results are returned to Spark).
+    qname_in / qname_out: queue names.
+    input_mapping: ``{column: tensor_name}``; when given, batches are dicts
+      ``{tensor_name: [column values]}`` with columns taken in ``sorted(input_mapping)`` order,
+      otherwise batches are lists of rows.
+  """
+
+  def __init__(self, mgr, train_mode=True, qname_in="input", qname_out="output",
+               input_mapping=None):
+    self.mgr = mgr
+    self.train_mode = train_mode
+    self.qname_in, self.qname_out = qname_in, qname_out
+    self.done_feeding = False
+    self.input_tensors = [t for _, t in sorted(input_mapping.items())] if input_mapping else None
+    self.queue_in = mgr.get_queue(qname_in)
+    self.queue_out = mgr.get_queue(qname_out) if not train_mode else None
+    self._rows = []        # rows of the block currently being drained
+    self._ring = None
+    self._prefetch = None
+
+  # ------------------------------------------------------------- internals
+  def _attach_ring(self):
+    if self._ring is None:
+      info = _value(self.mgr.get("ring"))
+      if not info:
+        raise RuntimeError("feeder posted a ring block but no ring is registered")
+      from . import shmring
+      self._ring = shmring.attach(info["name"])
+    return self._ring
+
+  def _expand(self, item):
+    """Turn one queue item into a list of rows.  Returns None for control markers."""
+    if isinstance(item, marker.RingBlock):
+      ring = self._attach_ring()
+      from . import shmring
+      rows = shmring.unpack_rows(ring, item)
+      ring.release_read(item.pos)
+      return rows
+    if isinstance(item, marker.Rows):
+      return item.rows
+    return [item]
+
+  def _pull(self):
+    """One blocking queue read.  Returns 'eof', 'end_partition' or 'rows'."""
+    item = self.queue_in.get(block=True)
+    if item is None:
+      logger.info("next_batch() got None: end of feed")
+      self.queue_in.task_done()
+      self.done_feeding = True
+      return "eof"
+    if isinstance(item, marker.EndPartition):
+      self.queue_in.task_done()
+      return "end_partition"
+    self._rows = self._expand(item)
+    self._rows.reverse()  # pop() from the end, preserving order
+    self.queue_in.task_done()
+    return "rows"
+
+  # ------------------------------------------------------------------- API
+  def next_batch(self, batch_size):
+    """Up to ``batch_size`` rows (fewer at end of feed / end of an inference partition)."""
+    tensors = [] if self.input_tensors is None else {t: [] for t in self.input_tensors}
+    count = 0
+    while count < batch_size:
+      if not self._rows:
+        if self.done_feeding:
+          break
+        what = self._pull()
+        if what == "eof":
+          break
+        if what == "end_partition":
+          if not self.train_mode and count > 0:
+            break
+          continue
+      while self._rows and count < batch_size:
+        row = self._rows.pop()
+        if self.input_tensors is None:
+          tensors.append(row)
+        else:
+          for i, t in enumerate(self.input_tensors):
+            tensors[t].append(row[i])
+        count += 1
+    return tensors
+
+  def should_stop(self):
+    """True once the end-of-feed marker has been consumed."""
+    return self.done_feeding and not self._rows
+
+  def batch_results(self, results):
+    """Return one result per input row of the last batch to Spark (inference mode)."""
+    results = list(results)
+    self.queue_out.put(marker.Rows(results), block=True)
+
+  def terminate(self):
+    """Stop consuming: flag the executor as terminating and drain whatever is still queued."""
+    logger.info("terminate() invoked")
+    self.mgr.set("state", "terminating")
+    self._rows = []
+    dropped = 0
+    while True:
+      try:
+        item = self.queue_in.get(block=True, timeout=5)
+        if isinstance(item, marker.RingBlock):
+          try:
+            self._attach_ring().release_read(item.pos)
+          except Exception:
+            pass
+        self.queue_in.task_done()
+        dropped += 1
+      except _queue_mod.Empty:
+        break
+    logger.info("dropped %d queued item(s)", dropped)
+
+  # -------------------------------------------------------- device fast path
+  def next_batch_tensors(self, batch_size, device=None, dtypes=None):
+    """Like :meth:`next_batch` but returns one device tensor per column.
+
+    Rows are staged in page-locked host memory and copied with ``cudaMemcpyAsync`` on a side
+    stream (feed.DevicePrefetcher); on a CPU-only host plain tensors are returned.
+    """
+    import numpy as np
+    import torch
+    batch = self.next_batch(batch_size)
+    if self.input_tensors is None:
+      cols = list(zip(*batch)) if batch and isinstance(batch[0], (list, tuple)) else [batch]
+      names = list(range(len(cols)))
+    else:
+      names = self.input_tensors
+      cols = [batch[t] for t in names]
+    out = []
+    use_cuda = torch.cuda.is_available() and (device is None or str(device).startswith("cuda"))
+    for i, c in enumerate(cols):
+      arr = np.asarray(c, dtype=(dtypes[i] if dtypes else None))
+      t = torch.from_numpy(np.ascontiguousarray(arr))
+      if use_cuda:
+        t = t.pin_memory().to(device or "cuda", non_blocking=True)
+      out.append(t)
+    return out if self.input_tensors is None else dict(zip(names, out))

@@ -1,0 +1,74 @@
+"""Host -> device input pipeline: pinned staging + side-stream copies.
+
+``DevicePrefetcher`` is the device half of the InputMode.SPARK fast path: batches
+arrive in page-locked host memory (either plain pinned tensors or slots of the
+shared-memory ring written by feeder tasks, csrc/feed.cc), are copied with
+``cudaMemcpyAsync`` on a dedicated copy stream into a small pool of device
+staging buffers, and are handed to the compute stream through CUDA events - the
+copy of batch i+1 overlaps the training step of batch i.
+
+The reference has no equivalent: rows cross two process boundaries one pickled
+RPC at a time and reach TF through ``tf.data.Dataset.from_generator``
+(tensorflowonspark/TFNode.py:278-300, examples/mnist/keras/mnist_spark.py:33-47).
+"""
+import collections
+
+import torch
+
+
+class DevicePrefetcher(object):
+
+  def __init__(self, specs, device, depth=2):
+    """specs: list of (shape, dtype) for the tensors of one batch."""
+    self.device = torch.device(device)
+    self.depth = depth
+    self.copy_stream = torch.cuda.Stream(device=self.device)
+    self.slots = [[torch.empty(s, dtype=dt, device=self.device) for (s, dt) in specs]
+                  for _ in range(depth)]
+    self.ready = [torch.cuda.Event() for _ in range(depth)]
+    self.consumed = [torch.cuda.Event() for _ in range(depth)]
+    self._used = [False] * depth
+    self._w = 0
+    self._queue = collections.deque()
+    self.bytes_per_batch = sum(int(torch.empty(s, dtype=dt).numel()) * torch.empty(0, dtype=dt)
+                               .element_size() for (s, dt) in specs)
+
+  def push(self, host_tensors):
+    """Enqueue an async copy of one batch (pinned host tensors) into the next staging slot."""
+    i = self._w
+    self._w = (self._w + 1) % self.depth
+    with torch.cuda.stream(self.copy_stream):
+      if self._used[i]:
+        self.copy_stream.wait_event(self.consumed[i])
+      for dst, src in zip(self.slots[i], host_tensors):
+        dst.copy_(src, non_blocking=True)
+      self.ready[i].record(self.copy_stream)
+    self._used[i] = True
+    self._queue.append(i)
+
+  def push_ring_slot(self, ring, pos, layout):
+    """Same, straight from a pinned shared-memory ring slot.  layout: [(offset, nbytes)] per tensor."""
+    i = self._w
+    self._w = (self._w + 1) % self.depth
+    with torch.cuda.stream(self.copy_stream):
+      if self._used[i]:
+        self.copy_stream.wait_event(self.consumed[i])
+      for dst, (off, nbytes) in zip(self.slots[i], layout):
+        ring.h2d(pos, off, dst.data_ptr(), nbytes, self.copy_stream.cuda_stream)
+      self.ready[i].record(self.copy_stream)
+    self._used[i] = True
+    self._queue.append(i)
+
+  def pop(self):
+    """Device tensors of the oldest pushed batch; the current stream waits for its copy."""
+    i = self._queue.popleft()
+    torch.cuda.current_stream(self.device).wait_event(self.ready[i])
+    self._last = i
+    return self.slots[i]
+
+  def release(self):
+    """Mark the batch returned by the last pop() as consumed (after the kernels reading it are enqueued)."""
+    self.consumed[self._last].record(torch.cuda.current_stream(self.device))
+
+  def pending(self):
+    return len(self._queue)

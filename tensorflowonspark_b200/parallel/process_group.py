@@ -1,0 +1,51 @@
+"""Process-group bring-up from a TFNodeContext.
+
+The node runtime (TFSparkNode._export_dist_env) derives ``MASTER_ADDR/MASTER_PORT/RANK/
+WORLD_SIZE`` from the cluster spec - rank 0 is the chief/master (else worker 0) and the
+rendezvous port is the port that node *reserved* during registration, which is exactly what
+the reference reserved it for (tensorflowonspark/TFSparkNode.py:343-352, there to hand to
+``tf.train.Server``).  NCCL is used when the node owns a GPU, gloo otherwise.
+"""
+import datetime
+import logging
+import os
+
+logger = logging.getLogger(__name__)
+
+
+def init_from_ctx(ctx, backend=None, timeout_s=1800):
+  import torch
+  import torch.distributed as dist
+  if ctx.rank < 0:
+    raise RuntimeError("{}:{} is not a worker rank".format(ctx.job_name, ctx.task_index))
+  if dist.is_initialized():
+    return dist.group.WORLD
+  if getattr(ctx, "tmp_socket", None) is not None:
+    ctx.release_port()  # the reserved port becomes the rendezvous port
+  use_cuda = bool(ctx.gpus) and torch.cuda.is_available()
+  backend = backend or ("nccl" if use_cuda else "gloo")
+  kwargs = {}
+  if use_cuda:
+    torch.cuda.set_device(0)
+    if backend == "nccl":
+      kwargs["device_id"] = torch.device("cuda", 0)
+  logger.info("init_process_group(%s) rank %d/%d at %s:%s", backend, ctx.rank, ctx.world_size,
+              os.environ.get("MASTER_ADDR"), os.environ.get("MASTER_PORT"))
+  dist.init_process_group(backend, rank=ctx.rank, world_size=ctx.world_size,
+                          timeout=datetime.timedelta(seconds=timeout_s), **kwargs)
+  return dist.group.WORLD
+
+
+def symm_from_ctx(ctx):
+  """SymmComm whose handle exchange runs over the reservation server's key/value board."""
+  from .. import reservation
+  from . import symm
+  client = reservation.Client(ctx.server_addr)
+  counter = [0]
+
+  def exchange(obj):
+    counter[0] += 1
+    tag = "symm/{}/{}".format(ctx.cluster_id, counter[0])
+    return client.all_gather(tag, ctx.rank, ctx.world_size, obj)
+
+  return symm.SymmComm(ctx.rank, ctx.world_size, exchange, ctx.device)

@@ -1,0 +1,151 @@
+"""Checkpoint / resume and the inference artefact format.
+
+The reference delegates all of this to TensorFlow in user code and only contributes path
+helpers and the ``grace_secs`` window (Keras ``ModelCheckpoint`` in
+examples/mnist/keras/mnist_spark.py:51-53, Estimator ``save_checkpoints_steps`` in
+examples/mnist/estimator/mnist_spark.py:94-97, SavedModel export via compat.py:10-17).
+Here:
+
+* ``save(model_dir, step, state)`` / ``latest_checkpoint`` / ``load`` - atomic (write to a
+  temp name, fsync, rename) ``ckpt-<step>.pt`` files plus a ``checkpoint`` index, so a restarted
+  job resumes from the newest complete file;
+* ``export_model`` / ``load_model`` - ``export_dir/{weights.pt, signature.json}``; the JSON keeps
+  the meaning of the pipeline params ``signature_def_key`` / ``tag_set`` / input & output
+  mappings (tensorflowonspark/pipeline.py:244-296).
+"""
+import json
+import logging
+import os
+import re
+import tempfile
+
+logger = logging.getLogger(__name__)
+
+INDEX = "checkpoint"
+
+
+def _local(path):
+  return path[len("file://"):] if path.startswith("file://") else path
+
+
+def _atomic_torch_save(obj, path):
+  import torch
+  d = os.path.dirname(path) or "."
+  os.makedirs(d, exist_ok=True)
+  fd, tmp = tempfile.mkstemp(dir=d, prefix=".tmp-", suffix=".pt")
+  try:
+    with os.fdopen(fd, "wb") as f:
+      torch.save(obj, f)
+      f.flush()
+      os.fsync(f.fileno())
+    os.replace(tmp, path)
+  except Exception:
+    if os.path.exists(tmp):
+      os.remove(tmp)
+    raise
+
+
+def save(model_dir, step, state, keep=5):
+  """Write ``state`` (any picklable / tensor dict) as checkpoint ``step``; prune old ones."""
+  model_dir = _local(model_dir)
+  path = os.path.join(model_dir, "ckpt-{:08d}.pt".format(int(step)))
+  _atomic_torch_save({"step": int(step), "state": state}, path)
+  tmp = os.path.join(model_dir, "." + INDEX + ".tmp")
+  with open(tmp, "w") as f:
+    json.dump({"latest": os.path.basename(path), "step": int(step)}, f)
+  os.replace(tmp, os.path.join(model_dir, INDEX))
+  ckpts = sorted(f for f in os.listdir(model_dir) if re.match(r"ckpt-\d+\.pt$", f))
+  for old in ckpts[:-keep] if keep else []:
+    try:
+      os.remove(os.path.join(model_dir, old))
+    except OSError:
+      pass
+  return path
+
+
+def latest_checkpoint(model_dir):
+  """Path of the newest complete checkpoint in ``model_dir`` or None."""
+  model_dir = _local(model_dir)
+  if not os.path.isdir(model_dir):
+    return None
+  idx = os.path.join(model_dir, INDEX)
+  if os.path.exists(idx):
+    try:
+      with open(idx) as f:
+        p = os.path.join(model_dir, json.load(f)["latest"])
+      if os.path.exists(p):
+        return p
+    except Exception:
+      pass
+  ckpts = sorted(f for f in os.listdir(model_dir) if re.match(r"ckpt-\d+\.pt$", f))
+  return os.path.join(model_dir, ckpts[-1]) if ckpts else None
+
+
+def load(path_or_dir, map_location="cpu"):
+  """(step, state) of a checkpoint file, or of the latest one in a directory; (0, None) if none."""
+  import torch
+  p = _local(path_or_dir)
+  if os.path.isdir(p):
+    p = latest_checkpoint(p)
+  if not p or not os.path.exists(p):
+    return 0, None
+  blob = torch.load(p, map_location=map_location, weights_only=False)
+  return blob["step"], blob["state"]
+
+
+def _state_of(model):
+  if hasattr(model, "state_dict"):
+    return model.state_dict()
+  if isinstance(model, dict):
+    return model
+  raise TypeError("cannot export object of type {}".format(type(model)))
+
+
+def export_model(model, export_dir, tag_set="serve", signatures=None, builder=None):
+  """Write the inference artefact.
+
+  Args:
+    model: object with ``state_dict()`` (torch module / native-engine model) or a state dict.
+    export_dir: target directory (``file://`` prefix allowed).
+    tag_set: tag(s) stored with the artefact (string or list).
+    signatures: ``{key: {'inputs': {alias: name}, 'outputs': {alias: name}}}``.
+    builder: dotted ``module:function`` that rebuilds the model for loading
+      (``fn(state_dict, **builder_args) -> callable``); defaults to the model's
+      ``export_builder`` attribute when present.
+  """
+  export_dir = _local(export_dir)
+  os.makedirs(export_dir, exist_ok=True)
+  _atomic_torch_save(_state_of(model), os.path.join(export_dir, "weights.pt"))
+  sig = {
+      "tag_set": tag_set if isinstance(tag_set, (list, tuple)) else str(tag_set).split(","),
+      "signatures": signatures or {"serving_default": {"inputs": {}, "outputs": {}}},
+      "builder": builder or getattr(model, "export_builder", None),
+      "builder_args": getattr(model, "export_builder_args", {}),
+  }
+  tmp = os.path.join(export_dir, ".signature.tmp")
+  with open(tmp, "w") as f:
+    json.dump(sig, f, indent=1)
+  os.replace(tmp, os.path.join(export_dir, "signature.json"))
+  logger.info("exported model to %s", export_dir)
+  return export_dir
+
+
+def load_model(export_dir, tag_set=None, map_location="cpu"):
+  """(callable_or_state_dict, signature_json) from an exported artefact."""
+  import importlib
+  import torch
+  export_dir = _local(export_dir)
+  with open(os.path.join(export_dir, "signature.json")) as f:
+    sig = json.load(f)
+  if tag_set:
+    want = tag_set if isinstance(tag_set, (list, tuple)) else str(tag_set).split(",")
+    if not set(want) <= set(sig["tag_set"]):
+      raise ValueError("export at {} has tags {}, requested {}".format(export_dir, sig["tag_set"],
+                                                                       want))
+  state = torch.load(os.path.join(export_dir, "weights.pt"), map_location=map_location,
+                     weights_only=False)
+  if sig.get("builder"):
+    mod, fn = sig["builder"].split(":")
+    model = getattr(importlib.import_module(mod), fn)(state, **sig.get("builder_args", {}))
+    return model, sig
+  return state, sig
