@@ -213,6 +213,13 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (fast) {
         __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(a.out);
         const bool relu_early = a.relu && !a.accumulate;
+        // per-tile row bookkeeping for the coalesced store phase: lane handles rows
+        // i*4 + (lane >> 3), i = 0..7; fetch their offsets / validity once, not per slab
+        const uint32_t vmask = __ballot_sync(0xffffffff, valid);
+        const bool zero_invalid = do_stats && vmask != 0xffffffffu;
+        long long roffs[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) roffs[i] = __shfl_sync(0xffffffff, off, i * 4 + (lane >> 3));
 #pragma unroll 1
         for (int c = half; c < BN / 64; c += 2) {
           uint32_t v[64];
@@ -236,7 +243,11 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               f0 = fmaxf(f0, 0.f);
               f1 = fmaxf(f1, 0.f);
             }
-            pk[j >> 1] = (do_stats && !valid) ? 0u : pack_bf16x2(f0, f1);
+            pk[j >> 1] = pack_bf16x2(f0, f1);
+          }
+          if (zero_invalid && !valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) pk[j] = 0u;
           }
 #pragma unroll
           for (int sgm = 0; sgm < 8; ++sgm) {
@@ -250,21 +261,23 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             // lane l owns columns (2l, 2l+1) of the slab: word (l & 3) of segment (l >> 2);
             // all lanes read the same row -> 32 distinct banks.  Statistics are taken of the
             // rounded values that are stored; rows outside the tensor were zeroed above.
-            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-#pragma unroll 8
+            float2 sacc = make_float2(0.f, 0.f), qacc = make_float2(0.f, 0.f);
+            const uint32_t lbase = stg + ((lane & 3) << 2);
+#pragma unroll
             for (int r = 0; r < 32; ++r) {
               uint32_t wv;
-              const uint32_t addr = stg + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2));
+              const uint32_t addr = lbase + r * 128 + (((lane >> 2) ^ (r & 7)) << 4);
               asm volatile("ld.shared.b32 %0, [%1];" : "=r"(wv) : "r"(addr));
-              const float2 xy = unpack_bf16x2(wv);
-              s0 += xy.x, s1 += xy.y;
-              q0 += xy.x * xy.x, q1 += xy.y * xy.y;
+              const float2 xy = make_float2(__uint_as_float(wv << 16),
+                                            __uint_as_float(wv & 0xffff0000u));
+              sacc = __fadd2_rn(sacc, xy);        // packed fp32x2 pipe (sm_100)
+              qacc = __ffma2_rn(xy, xy, qacc);
             }
             float* st = stat_smem + (c * 64 + 2 * lane) * 2;
-            red_shared_add(st + 0, s0);
-            red_shared_add(st + 1, q0);
-            red_shared_add(st + 2, s1);
-            red_shared_add(st + 3, q1);
+            red_shared_add(st + 0, sacc.x);
+            red_shared_add(st + 1, qacc.x);
+            red_shared_add(st + 2, sacc.y);
+            red_shared_add(st + 3, qacc.y);
           }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -274,9 +287,8 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                          : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
                          : "r"(addr));
-            const long long roff = __shfl_sync(0xffffffff, off, r2);
-            const int rvalid = __shfl_sync(0xffffffff, static_cast<int>(valid), r2);
-            if (rvalid) {
+            const long long roff = roffs[i];
+            if ((vmask >> r2) & 1u) {
               __nv_bfloat16* o = obase + roff + c * 64 + sg2 * 8;
               if (a.accumulate) {
                 const uint4 p = *reinterpret_cast<const uint4*>(o);

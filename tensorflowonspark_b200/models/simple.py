@@ -1,0 +1,54 @@
+"""Small dense models for the Spark-ML pipeline path (reference tests/test_pipeline.py:89-172
+trains a one-unit linear regression through TFEstimator and serves it with TFModel)."""
+import torch
+
+
+class Linear(torch.nn.Module):
+  """y = x W^T + b with the export hooks TFModel needs to rebuild it on the executors."""
+
+  export_builder = "tensorflowonspark_b200.models.simple:build_linear"
+
+  def __init__(self, in_features=2, out_features=1, input_name="x", output_name="y"):
+    super(Linear, self).__init__()
+    self.fc = torch.nn.Linear(in_features, out_features)
+    self.export_builder_args = {"in_features": in_features, "out_features": out_features,
+                                "input_name": input_name, "output_name": output_name}
+
+  def forward(self, x):
+    return self.fc(x)
+
+
+class _Served(object):
+  """Callable taking named numpy inputs and returning named outputs (the 'signature')."""
+
+  def __init__(self, module, input_name, output_name, device):
+    self.module, self.input_name, self.output_name, self.device = module, input_name, output_name, device
+
+  def __call__(self, **inputs):
+    x = torch.as_tensor(inputs[self.input_name], dtype=torch.float32, device=self.device)
+    with torch.no_grad():
+      return {self.output_name: self.module(x)}
+
+
+def build_linear(state, in_features=2, out_features=1, input_name="x", output_name="y"):
+  m = Linear(in_features, out_features, input_name, output_name)
+  m.load_state_dict(state)
+  dev = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
+  return _Served(m.to(dev).eval(), input_name, output_name, dev)
+
+
+def allreduce_mean_grads(module, world_size):
+  """Plain torch.distributed gradient averaging (the CPU/gloo plumbing path and the NCCL
+  baseline; the B200 product path is parallel/fused_optim.py)."""
+  import torch.distributed as dist
+  if world_size <= 1:
+    return
+  flat = torch.cat([p.grad.reshape(-1) for p in module.parameters() if p.grad is not None])
+  dist.all_reduce(flat)
+  flat /= world_size
+  off = 0
+  for p in module.parameters():
+    if p.grad is not None:
+      n = p.grad.numel()
+      p.grad.copy_(flat[off:off + n].view_as(p.grad))
+      off += n

@@ -1,0 +1,147 @@
+"""Cluster life-cycle on 2 executor processes (scenarios of reference tests/test_TFCluster.py:16-121
+plus ps / evaluator / epochs / terminate paths the reference never tested)."""
+import time
+
+import pytest
+
+from tensorflowonspark_b200 import TFCluster, TFNode
+
+
+def test_independent_nodes(sc):
+  def fn(args, ctx):
+    assert args["x"] + args["y"] == 3
+
+  cluster = TFCluster.run(sc, fn, {"x": 1, "y": 2}, 2, 0)
+  cluster.shutdown()
+
+
+def test_inputmode_spark_inference_roundtrip(sc):
+  def fn(args, ctx):
+    import numpy as np
+    feed = TFNode.DataFeed(ctx.mgr, False)
+    while not feed.should_stop():
+      batch = feed.next_batch(10)
+      if len(batch) > 0:
+        feed.batch_results(np.square(np.array(batch)).tolist())
+
+  rdd = sc.parallelize([[x] for x in range(1000)], 10)
+  cluster = TFCluster.run(sc, fn, {}, 2, 0, input_mode=TFCluster.InputMode.SPARK)
+  out = cluster.inference(rdd)
+  assert out.map(lambda r: r[0]).sum() == sum(x * x for x in range(1000))
+  cluster.shutdown()
+
+
+def test_train_epochs_and_terminate(sc):
+  def fn(args, ctx):
+    feed = ctx.get_data_feed(train_mode=True)
+    seen = 0
+    while not feed.should_stop() and seen < 300:
+      seen += len(feed.next_batch(50))
+    with open(args["out"] + str(ctx.executor_id), "w") as f:
+      f.write(str(seen))
+    feed.terminate()
+
+  import tempfile
+  out = tempfile.mkdtemp() + "/seen"
+  cluster = TFCluster.run(sc, fn, {"out": out}, 2, 0, input_mode=TFCluster.InputMode.SPARK)
+  cluster.train(sc.parallelize(range(200), 4), num_epochs=5)  # 1000 rows offered, 600 consumed
+  cluster.shutdown()
+  assert [int(open(out + str(i)).read()) for i in range(2)] == [300, 300]
+
+
+def test_exception_during_feed_reaches_driver(sc):
+  def fn(args, ctx):
+    feed = TFNode.DataFeed(ctx.mgr, False)
+    while not feed.should_stop():
+      batch = feed.next_batch(10)
+      if len(batch) > 0:
+        feed.batch_results(batch)
+        raise Exception("FAKE exception during feeding")
+
+  rdd = sc.parallelize([[x] for x in range(1000)], 10)
+  with pytest.raises(Exception, match="FAKE exception during feeding|Timeout"):
+    cluster = TFCluster.run(sc, fn, {}, 2, 0, input_mode=TFCluster.InputMode.SPARK)
+    cluster.inference(rdd, feed_timeout=2).count()
+  try:
+    cluster.shutdown()
+  except Exception:
+    pass
+
+
+def test_late_exception_caught_by_shutdown(sc):
+  def fn(args, ctx):
+    feed = TFNode.DataFeed(ctx.mgr, False)
+    while not feed.should_stop():
+      batch = feed.next_batch(10)
+      if len(batch) > 0:
+        feed.batch_results(batch)
+    time.sleep(1)
+    raise Exception("FAKE exception after feeding")
+
+  rdd = sc.parallelize([[x] for x in range(100)], 4)
+  cluster = TFCluster.run(sc, fn, {}, 2, 0, input_mode=TFCluster.InputMode.SPARK)
+  cluster.inference(rdd).count()
+  with pytest.raises(Exception, match="FAKE exception after feeding"):
+    cluster.shutdown(grace_secs=3)
+
+
+def test_port_released(sc):
+  def fn(args, ctx):
+    assert ctx.tmp_socket is None
+
+  TFCluster.run(sc, fn, {}, 2, 0, input_mode=TFCluster.InputMode.TENSORFLOW,
+                master_node="chief").shutdown()
+
+
+def test_port_unreleased(sc):
+  def fn(args, ctx):
+    import socket
+    assert ctx.tmp_socket is not None
+    port = ctx.tmp_socket.getsockname()[1]
+    s = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
+    try:
+      s.bind(("0.0.0.0", port))
+      raise AssertionError("reserved port could be bound twice")
+    except socket.error:
+      pass
+    ctx.release_port()
+    assert ctx.tmp_socket is None
+
+  TFCluster.run(sc, fn, {}, 2, 0, input_mode=TFCluster.InputMode.TENSORFLOW, master_node="chief",
+                release_port=False).shutdown()
+
+
+def test_roles_ps_and_chief(sc):
+  import tempfile
+  d = tempfile.mkdtemp()
+
+  def fn(args, ctx):
+    with open("{}/{}-{}".format(args["d"], ctx.job_name, ctx.task_index), "w") as f:
+      f.write("{} {}".format(ctx.rank, sorted(ctx.cluster_spec)))
+    if ctx.job_name == "ps":
+      time.sleep(600)  # parked until the driver stops it through the control queue
+
+  cluster = TFCluster.run(sc, fn, {"d": d}, 2, 1, input_mode=TFCluster.InputMode.TENSORFLOW,
+                          master_node="chief")
+  assert sorted(n["job_name"] for n in cluster.cluster_info) == ["chief", "ps"]
+  cluster.shutdown()
+  import os
+  assert sorted(os.listdir(d)) == ["chief-0", "ps-0"]
+  assert open(d + "/chief-0").read().startswith("0 ")
+  assert open(d + "/ps-0").read().startswith("-1 ")
+
+
+def test_size_and_mode_validation(sc):
+  with pytest.raises(Exception, match="InputMode.TENSORFLOW"):
+    TFCluster.run(sc, lambda a, c: None, {}, 2, 0, input_mode=TFCluster.InputMode.SPARK,
+                  eval_node=True)
+  with pytest.raises(AssertionError):
+    TFCluster.run(sc, lambda a, c: None, {}, 2, 2)
+
+
+def test_argv_list_becomes_sys_argv(sc):
+  def fn(argv, ctx):
+    import sys
+    assert sys.argv == ["prog", "--flag", "1"] and argv == sys.argv
+
+  TFCluster.run(sc, fn, ["prog", "--flag", "1"], 2, 0).shutdown()

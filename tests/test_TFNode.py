@@ -1,0 +1,96 @@
+"""TFNode helpers (scenarios of reference tests/test_TFNode.py:8-58) + ring/chunk feed paths."""
+import getpass
+import os
+
+from tensorflowonspark_b200 import TFManager, TFNode, marker, shmring
+
+
+def test_hdfs_path():
+  cwd, user = os.getcwd(), getpass.getuser()
+  fs = ["file://", "hdfs://", "viewfs://"]
+  paths = {
+      "hdfs://foo/bar": ["hdfs://foo/bar"] * 3,
+      "viewfs://foo/bar": ["viewfs://foo/bar"] * 3,
+      "file://foo/bar": ["file://foo/bar"] * 3,
+      "/foo/bar": ["file:///foo/bar", "hdfs:///foo/bar", "viewfs:///foo/bar"],
+      "foo/bar": ["file://{}/foo/bar".format(cwd), "hdfs:///user/{}/foo/bar".format(user),
+                  "viewfs:///user/{}/foo/bar".format(user)],
+  }
+  for i, f in enumerate(fs):
+    ctx = type("MockContext", (), {"defaultFS": f, "working_dir": cwd})
+    for path, expected in paths.items():
+      assert TFNode.hdfs_path(ctx, path) == expected[i]
+
+
+def test_datafeed_row_items():
+  mgr = TFManager.start(b"abc", ["input", "output"], "local")
+  q = mgr.get_queue("input")
+  for i in range(10):
+    q.put(i)
+  q.put(None)
+  feed = TFNode.DataFeed(mgr)
+  assert len(feed.next_batch(2)) == 2
+  assert len(feed.next_batch(4)) == 4
+  assert not feed.should_stop()
+  assert len(feed.next_batch(10)) == 4  # short batch at end of feed
+  assert feed.should_stop()
+  mgr.shutdown()
+
+
+def test_datafeed_chunks_mapping_and_partitions():
+  mgr = TFManager.start(b"abc", ["input", "output"], "local")
+  q = mgr.get_queue("input")
+  q.put(marker.Rows([[i, i * 2] for i in range(5)]))
+  q.put(marker.EndPartition())
+  q.put(marker.Rows([[i, i * 2] for i in range(5, 8)]))
+  q.put(marker.EndPartition())
+  q.put(None)
+  feed = TFNode.DataFeed(mgr, train_mode=False, input_mapping={"a": "x", "b": "y"})
+  b = feed.next_batch(4)
+  assert b == {"x": [0, 1, 2, 3], "y": [0, 2, 4, 6]}
+  assert feed.next_batch(4) == {"x": [4], "y": [8]}  # stops at the partition boundary
+  feed.batch_results([1, 2, 3])
+  assert mgr.get_queue("output").get().rows == [1, 2, 3]
+  assert feed.next_batch(4) == {"x": [5, 6, 7], "y": [10, 12, 14]}
+  assert feed.next_batch(4) == {"x": [], "y": []} and feed.should_stop()
+  mgr.shutdown()
+
+
+def test_datafeed_ring_blocks():
+  mgr = TFManager.start(b"abc", ["input", "output"], "local")
+  name, ring = shmring.create(4, 1 << 20)
+  mgr.set("ring", {"name": name, "nslots": 4, "slot_bytes": 1 << 20})
+  rows = [[float(i), [i, i + 1, i + 2]] for i in range(100)]
+  blk = shmring.pack_rows(ring, rows)
+  assert isinstance(blk, marker.RingBlock) and blk.nrows == 100
+  assert shmring.pack_rows(ring, [["a", 1]]) is None  # non-numeric rows use the queue path
+  q = mgr.get_queue("input")
+  q.put(blk)
+  q.put(None)
+  feed = TFNode.DataFeed(mgr)
+  got = feed.next_batch(64) + feed.next_batch(64)
+  assert got == rows and feed.should_stop()
+  # the consumed slot was released: the 4-slot ring accepts 4 more blocks without blocking
+  for _ in range(4):
+    assert shmring.pack_rows(ring, rows[:3], timeout=2.0) is not None
+  mgr.shutdown()
+
+
+def test_terminate_drains_queue():
+  mgr = TFManager.start(b"abc", ["input", "output"], "local")
+  q = mgr.get_queue("input")
+  for i in range(5):
+    q.put(i)
+  feed = TFNode.DataFeed(mgr)
+  feed.next_batch(2)
+  import tensorflowonspark_b200.TFNode as tfn
+  orig = tfn._queue_mod.Empty
+  feed.queue_in.get  # noqa: B018
+  # shorten the idle timeout for the test
+  real_get = feed.queue_in.get
+  feed.queue_in.get = lambda block=True, timeout=5: real_get(block, 0.3)
+  feed.terminate()
+  assert str(mgr.get("state")).strip("'") == "terminating"
+  q.join()  # every queued item was task_done()'d
+  assert orig is tfn._queue_mod.Empty
+  mgr.shutdown()

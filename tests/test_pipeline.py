@@ -1,0 +1,122 @@
+"""Spark-ML pipeline layer (scenarios of reference tests/test_pipeline.py:48-172): Namespace,
+param merging, and an end-to-end distributed fit -> export -> transform on 2 CPU executors
+(gloo all-reduce standing in for MultiWorkerMirroredStrategy)."""
+import argparse
+import os
+
+import numpy as np
+import pytest
+
+from tensorflowonspark_b200 import TFCluster
+from tensorflowonspark_b200.pipeline import (HasBatchSize, HasSteps, Namespace, TFEstimator, TFModel,
+                                             TFParams, yield_batch)
+
+
+def test_namespace():
+  d = {"string": "foo", "integer": 1, "float": 3.14, "array": [1, 2, 3], "map": {"a": 1, "b": 2}}
+  n1 = Namespace(d)
+  assert (n1.string, n1.integer, n1.float, n1.array, n1.map) == ("foo", 1, 3.14, [1, 2, 3],
+                                                                 {"a": 1, "b": 2})
+  assert "string" in n1 and "extra" not in n1
+  n2 = Namespace(n1)
+  assert n2 == n1 and n2.map == {"a": 1, "b": 2}
+  n3 = Namespace(argparse.Namespace(x=1))
+  assert n3.x == 1
+  argv = ["--foo", "1", "--bar", "test", "--baz", "3.14"]
+  assert Namespace(argv).argv == argv
+  with pytest.raises(Exception):
+    Namespace(42)
+
+
+def test_merge_args_params():
+  class Foo(TFParams, HasBatchSize, HasSteps):
+    def __init__(self, args):
+      super(Foo, self).__init__()
+      self.args = args
+
+  f = Foo(Namespace({"a": 1, "b": 2})).setBatchSize(10).setSteps(100)
+  assert f.merge_args_params() == Namespace({"a": 1, "b": 2, "batch_size": 10, "steps": 100})
+  assert f.getBatchSize() == 10 and f.getSteps() == 100
+  with pytest.raises(TypeError):
+    f.setBatchSize("ten")
+
+
+def test_param_surface_and_defaults():
+  est = TFEstimator(lambda a, c: None, {})
+  pairs = ["BatchSize", "ClusterSize", "Epochs", "GraceSecs", "InputMapping", "InputMode",
+           "MasterNode", "ModelDir", "NumPS", "DriverPSNodes", "Protocol", "Readers", "Steps",
+           "Tensorboard", "TFRecordDir", "ExportDir"]
+  for p in pairs:
+    assert hasattr(est, "set" + p) and hasattr(est, "get" + p), p
+  assert (est.getClusterSize(), est.getNumPS(), est.getBatchSize(), est.getEpochs(), est.getSteps(),
+          est.getGraceSecs(), est.getMasterNode()) == (1, 0, 100, 1, 1000, 30, "chief")
+  assert est.getInputMode() == TFCluster.InputMode.SPARK
+  with pytest.raises(Exception, match="deprecated"):
+    est.setInputMode(TFCluster.InputMode.TENSORFLOW)
+  model = TFModel({})
+  for p in ["InputMapping", "OutputMapping", "BatchSize", "ModelDir", "ExportDir", "SignatureDefKey",
+            "TagSet"]:
+    assert hasattr(model, "set" + p) and hasattr(model, "get" + p), p
+
+
+def test_yield_batch():
+  rows = [(i, i * 2) for i in range(5)]
+  assert list(yield_batch(iter(rows), 2, 2)) == [[[0, 1], [0, 2]], [[2, 3], [4, 6]], [[4], [8]]]
+
+
+def _train_fn(args, ctx):
+  """Linear regression with sync data parallelism fed from Spark."""
+  import torch
+  from tensorflowonspark_b200 import compat
+  from tensorflowonspark_b200.models import simple
+  from tensorflowonspark_b200.utils import checkpoint
+  ctx.init_process_group(backend="gloo")
+  torch.manual_seed(0)
+  model = simple.Linear(2, 1, input_name="x", output_name="y")
+  opt = torch.optim.Adam(model.parameters(), lr=0.2)
+  sched = torch.optim.lr_scheduler.ExponentialLR(opt, gamma=1.0)
+  feed = ctx.get_data_feed(input_mapping=args.input_mapping)
+  # train 90% of the expected steps: partitions are uneven and every step is a collective
+  steps = int(1000 * args.epochs * 0.9 / (args.batch_size * ctx.num_workers))
+  for step in range(steps):
+    batch = feed.next_batch(args.batch_size)
+    x = torch.tensor(batch["x"], dtype=torch.float32)
+    y = torch.tensor(batch["y_"], dtype=torch.float32)
+    loss = torch.nn.functional.mse_loss(model(x), y)
+    opt.zero_grad()
+    loss.backward()
+    simple.allreduce_mean_grads(model, ctx.num_workers)
+    opt.step()
+    sched.step()
+  if ctx.is_chief and args.model_dir:
+    checkpoint.save(args.model_dir, steps, model.state_dict())
+  if args.export_dir:
+    compat.export_saved_model(model, args.export_dir, ctx.job_name == "chief", signatures={
+        "serving_default": {"inputs": {"x": "x"}, "outputs": {"y": "y"},
+                            "input_shapes": {"x": [-1, 2]}}})
+  feed.terminate()
+
+
+def test_estimator_fit_export_transform(sc, spark, tmp_path):
+  weights = np.array([3.14, 1.618])
+  rng = np.random.RandomState(0)
+  feats = rng.rand(1000, 2)
+  labels = feats @ weights
+  train = [(f.tolist(), [float(l)]) for f, l in zip(feats, labels)]
+  df = sc.parallelize(train, 2).toDF(["col1", "col2"])
+  model_dir, export_dir = str(tmp_path / "model"), str(tmp_path / "export")
+  est = TFEstimator(_train_fn, {}) \
+      .setInputMapping({"col1": "x", "col2": "y_"}) \
+      .setModelDir(model_dir).setExportDir(export_dir) \
+      .setClusterSize(2).setMasterNode("chief").setNumPS(0) \
+      .setBatchSize(5).setEpochs(4).setGraceSecs(2)
+  model = est.fit(df)
+  assert os.path.isdir(export_dir) and os.path.exists(os.path.join(export_dir, "signature.json"))
+  from tensorflowonspark_b200.utils import checkpoint
+  assert checkpoint.latest_checkpoint(model_dir) is not None
+
+  test_df = spark.createDataFrame([([1.0, 1.0], [0.0])], ["c1", "c2"])
+  model.setTagSet("serve").setSignatureDefKey("serving_default") \
+       .setInputMapping({"c1": "x"}).setOutputMapping({"y": "cout"})
+  pred = model.transform(test_df).head().cout[0]
+  assert abs(pred - weights.sum()) < 0.05, pred
