@@ -64,7 +64,7 @@ class ClusterServer(object):
         time.sleep(3600)
 
 
-def start_cluster_server(ctx, num_gpus=1, rdma=False, backend=None, async_ps=None):
+def start_cluster_server(ctx, num_gpus=1, rdma=False, backend=None, async_ps=None, params=None):
   """Join this node to the cluster's communication substrate.
 
   Returns ``(cluster_spec, server)`` like the reference.  With ``num_ps == 0`` every worker
@@ -79,7 +79,8 @@ def start_cluster_server(ctx, num_gpus=1, rdma=False, backend=None, async_ps=Non
     async_ps = has_ps
   if async_ps:
     from .parallel import ps as ps_mod
-    handle = ps_mod.attach(ctx)
+    # ps nodes need the parameter count (or initial values); workers just attach
+    handle = ps_mod.attach(ctx, params=params)
     return ctx.cluster_spec, ClusterServer(ctx, ps=handle)
   group = process_group.init_from_ctx(ctx, backend=backend)
   return ctx.cluster_spec, ClusterServer(ctx, group=group)
@@ -242,6 +243,17 @@ class DataFeed(object):
       except _queue_mod.Empty:
         break
     logger.info("dropped %d queued item(s)", dropped)
+    # Tell the driver right away.  (The reference only relays this through the *next* feeder
+    # task, tensorflowonspark/TFSparkNode.py:520-531, so a stream that goes quiet never stops.)
+    try:
+      addr = _value(self.mgr.get("server_addr"))
+      if addr:
+        from . import reservation
+        client = reservation.Client(tuple(addr))
+        client.request_stop()
+        client.close()
+    except Exception as e:
+      logger.debug("could not notify the reservation server: %s", e)
 
   # -------------------------------------------------------- device fast path
   def next_batch_tensors(self, batch_size, device=None, dtypes=None):

@@ -299,6 +299,7 @@ def run(fn, tf_args, cluster_meta, tensorboard, log_dir, queues, background):
       if background and os.environ.get("TFOS_FEED_RING", "1") == "1":
         _create_ring()
     TFSparkNode.mgr.set("state", "running")
+    TFSparkNode.mgr.set("server_addr", list(cluster_meta["server_addr"]))
     TFSparkNode.cluster_id = cluster_meta["id"]
 
     if "HADOOP_PREFIX" in os.environ and "TFOS_CLASSPATH_UPDATED" not in os.environ:

@@ -137,9 +137,18 @@ def new_name():
   return "/tfos_ring_{}_{}".format(os.getpid(), uuid.uuid4().hex[:8])
 
 
+def _unlink(name):
+  try:
+    os.unlink("/dev/shm/" + name.lstrip("/"))
+  except OSError:
+    pass
+
+
 def create(nslots=DEFAULT_SLOTS, slot_bytes=DEFAULT_SLOT_BYTES, name=None):
+  import atexit
   name = name or new_name()
   ring = _ring_cls()(name, True, nslots, slot_bytes)
+  atexit.register(_unlink, name)  # also covers executors torn down by SIGTERM
   return name, ring
 
 

@@ -158,7 +158,15 @@ def _executor_main(index, conn, app_dir, conf, env):
   except OSError:
     pass
   signal.signal(signal.SIGINT, signal.SIG_IGN)
-  signal.signal(signal.SIGTERM, lambda *_: sys.exit(0))  # run destructors (shared-memory rings)
+  def _on_term(*_):
+    # run the atexit hooks (they unlink shared-memory feed rings), then leave without unwinding
+    import atexit
+    try:
+      atexit._run_exitfuncs()
+    finally:
+      os._exit(0)
+
+  signal.signal(signal.SIGTERM, _on_term)
   cwd = os.path.join(app_dir, "executor-{}".format(index))
   os.makedirs(cwd, exist_ok=True)
   os.chdir(cwd)
