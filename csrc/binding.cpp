@@ -328,11 +328,33 @@ void conv3x3_c1_wgrad(const Tensor& x, const Tensor& dy, Tensor dw, c10::optiona
                                x.size(0), x.size(1), x.size(2), dy.size(3), cur_stream()),
         "conv3x3_c1_wgrad");
 }
-void depthwise3x3_fwd(const Tensor& x, const Tensor& w, Tensor y, int stride) {
+void depthwise3x3_fwd(const Tensor& x, const Tensor& w, c10::optional<Tensor> bias, Tensor y,
+                      int stride, int act) {
   need(x, torch::kBFloat16, "x");
-  check(tfos::depthwise3x3_fwd(x.data_ptr(), w.data_ptr(), y.data_ptr(), x.size(0), x.size(1),
-                               x.size(2), x.size(3), stride, cur_stream()),
+  check(tfos::depthwise3x3_fwd(x.data_ptr(), w.data_ptr(), optf(bias), y.data_ptr(), x.size(0),
+                               x.size(1), x.size(2), x.size(3), stride, act, cur_stream()),
         "depthwise3x3_fwd");
+}
+void copy_channels(const Tensor& src, Tensor dst, int C, int src_off, int dst_off) {
+  need(src, torch::kBFloat16, "src");
+  need(dst, torch::kBFloat16, "dst");
+  const int sld = src.size(-1), dld = dst.size(-1);
+  TORCH_CHECK(C % 8 == 0 && src_off % 8 == 0 && dst_off % 8 == 0 && sld % 8 == 0 && dld % 8 == 0,
+              "copy_channels: channel counts / offsets must be multiples of 8");
+  TORCH_CHECK(src.numel() / sld == dst.numel() / dld, "copy_channels: pixel counts differ");
+  check(tfos::copy_channels(src.data_ptr(), dst.data_ptr(), src.numel() / sld, C, sld, src_off,
+                            dld, dst_off, cur_stream()),
+        "copy_channels");
+}
+void pixel_xent(const Tensor& logits, const Tensor& labels, c10::optional<Tensor> dlogits,
+                Tensor loss_sum, c10::optional<Tensor> correct, int V, double scale) {
+  need(logits, torch::kBFloat16, "logits");
+  need(labels, torch::kInt32, "labels");
+  TORCH_CHECK(logits.size(-1) == 8 && V <= 8, "pixel_xent expects 8 padded channels");
+  check(tfos::pixel_xent(logits.data_ptr(), labels.data_ptr<int>(),
+                         const_cast<void*>(optptr(dlogits)), loss_sum.data_ptr<float>(),
+                         optf(correct), logits.numel() / 8, V, scale, cur_stream()),
+        "pixel_xent");
 }
 
 // --------------------------------------------------- collectives / optimizer
@@ -482,6 +504,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("conv3x3_c1_fwd", &conv3x3_c1_fwd);
   m.def("conv3x3_c1_wgrad", &conv3x3_c1_wgrad);
   m.def("depthwise3x3_fwd", &depthwise3x3_fwd);
+  m.def("copy_channels", &copy_channels);
+  m.def("pixel_xent", &pixel_xent);
   m.def("allreduce_opt", &allreduce_opt);
   m.def("bcast_pull", &bcast_pull);
   m.def("flag_barrier", &flag_barrier);

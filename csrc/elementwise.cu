@@ -580,6 +580,68 @@ cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ o
     out[i] = __float2bfloat16_rn(in[i]);
 }
 
+// Strided channel copy: dst[p, dst_off + c] = src[p, src_off + c], c < C (8-channel vectors).
+// Writes an activation into its slot of a channel-concatenated buffer and cuts the matching
+// slice out of the concatenated gradient on the way back (U-Net skip connections).
+__global__ void __launch_bounds__(256)
+copy_channels_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                     long long P, int C, int src_ld, int src_off, int dst_ld, int dst_off) {
+  const int groups = C >> 3;
+  const long long total = P * groups;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long p = i / groups;
+    const int g = static_cast<int>(i % groups);
+    *reinterpret_cast<uint4*>(dst + p * dst_ld + dst_off + g * 8) =
+        *reinterpret_cast<const uint4*>(src + p * src_ld + src_off + g * 8);
+  }
+}
+
+// Per-pixel softmax cross-entropy for a handful of classes (V <= 8): one thread per pixel, the
+// pixel's 8 padded logits are one 16-byte load.  loss_sum += -log p[label] * scale,
+// dlogits = (p - onehot) * scale, padded channels get zero gradient.
+__global__ void __launch_bounds__(256)
+pixel_xent_kernel(const __nv_bfloat16* __restrict__ logits, const int* __restrict__ labels,
+                  __nv_bfloat16* __restrict__ dlogits, float* loss_sum, float* correct_sum,
+                  long long P, int V, float scale) {
+  float local = 0.f, hits = 0.f;
+  for (long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; p < P;
+       p += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float l[8];
+    load8(logits + p * 8, l);
+    float mx = l[0];
+    int am = 0;
+#pragma unroll
+    for (int j = 1; j < 8; ++j)
+      if (j < V && l[j] > mx) mx = l[j], am = j;
+    float se = 0.f, e[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      e[j] = j < V ? __expf(l[j] - mx) : 0.f;
+      se += e[j];
+    }
+    const int label = labels[p];
+    const float inv = 1.f / se;
+    float lab_logit = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (j == label) lab_logit = l[j];
+      e[j] = j < V ? (e[j] * inv - (j == label ? 1.f : 0.f)) * scale : 0.f;
+    }
+    if (dlogits != nullptr) store8(dlogits + p * 8, e);
+    local += -(lab_logit - mx - __logf(se)) * scale;
+    hits += (am == label) ? 1.f : 0.f;
+  }
+  for (int o = 16; o >= 1; o >>= 1) {
+    local += __shfl_xor_sync(0xffffffff, local, o);
+    hits += __shfl_xor_sync(0xffffffff, hits, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(loss_sum, local);
+    if (correct_sum != nullptr) atomicAdd(correct_sum, hits);
+  }
+}
+
 inline int grid_for(long long work, int threads, int max_blocks) {
   long long b = (work + threads - 1) / threads;
   if (b < 1) b = 1;
@@ -718,6 +780,20 @@ cudaError_t decode_normalize(const uint8_t* in, void* out, int N, int H, int W, 
   decode_normalize_kernel<<<grid_for(total, 256, kMaxBlocks * 4), 256, 0, s>>>(
       in, static_cast<__nv_bfloat16*>(out), N, H, W, C, Wp, Cp, wofs, mean3[0], mean3[1], mean3[2],
       istd3[0], istd3[1], istd3[2]);
+  TFOS_RET();
+}
+cudaError_t copy_channels(const void* src, void* dst, long long P, int C, int src_ld, int src_off,
+                          int dst_ld, int dst_off, cudaStream_t s) {
+  copy_channels_kernel<<<grid_for(P * (C >> 3), 256, kMaxBlocks), 256, 0, s>>>(
+      static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), P, C, src_ld,
+      src_off, dst_ld, dst_off);
+  TFOS_RET();
+}
+cudaError_t pixel_xent(const void* logits, const int* labels, void* dlogits, float* loss_sum,
+                       float* correct_sum, long long P, int V, float scale, cudaStream_t s) {
+  pixel_xent_kernel<<<grid_for(P, 256, kMaxBlocks), 256, 0, s>>>(
+      static_cast<const __nv_bfloat16*>(logits), labels, static_cast<__nv_bfloat16*>(dlogits),
+      loss_sum, correct_sum, P, V, scale);
   TFOS_RET();
 }
 cudaError_t cast_f32_bf16(const float* in, void* out, long long n, cudaStream_t s) {

@@ -242,6 +242,10 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (relu_early) {
               f0 = fmaxf(f0, 0.f);
               f1 = fmaxf(f1, 0.f);
+              if (a.relu == 2) {  // ReLU6 (MobileNetV2 encoder)
+                f0 = fminf(f0, 6.f);
+                f1 = fminf(f1, 6.f);
+              }
             }
             pk[j >> 1] = pack_bf16x2(f0, f1);
           }
@@ -360,6 +364,10 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (a.relu) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+              if (a.relu == 2) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = fminf(f[j], 6.f);
+              }
             }
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = __bfloat162float(__float2bfloat16_rn(f[j]));

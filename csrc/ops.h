@@ -42,6 +42,10 @@ cudaError_t decode_normalize(const uint8_t* in, void* out, int N, int H, int W, 
                              int Cp, int wofs, const float* mean3, const float* istd3,
                              cudaStream_t s);
 cudaError_t cast_f32_bf16(const float* in, void* out, long long n, cudaStream_t s);
+cudaError_t copy_channels(const void* src, void* dst, long long P, int C, int src_ld, int src_off,
+                          int dst_ld, int dst_off, cudaStream_t s);
+cudaError_t pixel_xent(const void* logits, const int* labels, void* dlogits, float* loss_sum,
+                       float* correct_sum, long long P, int V, float scale, cudaStream_t s);
 
 // ---- optim_comm.cu
 constexpr int kMaxRanks = 8;
@@ -89,7 +93,7 @@ cudaError_t conv3x3_c1_fwd(const void* x, const void* w, const float* bias, void
                            int W, int Cout, int relu, cudaStream_t s);
 cudaError_t conv3x3_c1_wgrad(const void* x, const void* dy, float* dw, float* dbias, int N, int H,
                              int W, int Cout, cudaStream_t s);
-cudaError_t depthwise3x3_fwd(const void* x, const void* w, void* y, int N, int H, int W, int C,
-                             int stride, cudaStream_t s);
+cudaError_t depthwise3x3_fwd(const void* x, const void* w, const float* bias, void* y, int N,
+                             int H, int W, int C, int stride, int act, cudaStream_t s);
 
 }  // namespace tfos

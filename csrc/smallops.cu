@@ -105,8 +105,8 @@ conv3x3_c1_wgrad_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16
 // x [N,H,W,C], w [9,C] (tap-major), y [N,OH,OW,C]; pad 1
 __global__ void __launch_bounds__(256)
 depthwise3x3_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
-                        __nv_bfloat16* __restrict__ y, int N, int H, int W, int C, int OH, int OW,
-                        int stride) {
+                        const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, int N, int H,
+                        int W, int C, int OH, int OW, int stride, int act) {
   const int groups = C >> 3;
   const long long total = static_cast<long long>(N) * OH * OW * groups;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -137,6 +137,12 @@ depthwise3x3_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16
         acc[0] += x0.x * w0.x, acc[1] += x0.y * w0.y, acc[2] += x1.x * w1.x, acc[3] += x1.y * w1.y;
         acc[4] += x2.x * w2.x, acc[5] += x2.y * w2.y, acc[6] += x3.x * w3.x, acc[7] += x3.y * w3.y;
       }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (bias != nullptr) acc[j] += bias[g * 8 + j];  // folded inference batch-norm shift
+      if (act >= 1) acc[j] = fmaxf(acc[j], 0.f);
+      if (act == 2) acc[j] = fminf(acc[j], 6.f);
     }
     uint4 p;
     p.x = pack_bf16x2(acc[0], acc[1]);
@@ -174,13 +180,13 @@ cudaError_t conv3x3_c1_wgrad(const void* x, const void* dy, float* dw, float* db
       W, Cout);
   return cudaGetLastError();
 }
-cudaError_t depthwise3x3_fwd(const void* x, const void* w, void* y, int N, int H, int W, int C,
-                             int stride, cudaStream_t s) {
+cudaError_t depthwise3x3_fwd(const void* x, const void* w, const float* bias, void* y, int N,
+                             int H, int W, int C, int stride, int act, cudaStream_t s) {
   const int OH = (H - 1) / stride + 1, OW = (W - 1) / stride + 1;
   const long long total = static_cast<long long>(N) * OH * OW * (C >> 3);
   depthwise3x3_fwd_kernel<<<blocks_for(total), 256, 0, s>>>(
-      static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(w),
-      static_cast<__nv_bfloat16*>(y), N, H, W, C, OH, OW, stride);
+      static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(w), bias,
+      static_cast<__nv_bfloat16*>(y), N, H, W, C, OH, OW, stride, act);
   return cudaGetLastError();
 }
 

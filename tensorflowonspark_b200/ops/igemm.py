@@ -202,7 +202,7 @@ def conv_fprop(x, w, y, stride=1, pad=0, bias=None, relu=False, stats=None):
       R, S, stride, Cin, Cout, OH, OW))
 
 
-def conv_dgrad(dy, w, dx, stride=1, pad=0, accumulate=False, relu=False, bias=None):
+def conv_dgrad(dy, w, dx, stride=1, pad=0, accumulate=False, relu=False, bias=None, stats=None):
   """dx[N,H,W,Cin] (=|+=) conv_transpose(dy[N,OH,OW,Cout], w[Cout,R,S,Cin]).
 
   Also the forward of a transposed convolution (Keras Conv2DTranspose) when
@@ -241,8 +241,9 @@ def conv_dgrad(dy, w, dx, stride=1, pad=0, accumulate=False, relu=False, bias=No
         "ldo": Cin, "n_valid": Cin, "accumulate": int(accumulate), "relu": int(relu),
         "bias": bias.data_ptr() if bias is not None else 0, "out": dx.data_ptr(),
     }
+    _stats_args(g, stats)  # transposed-conv *forward* feeding a batch norm
     handles.append(_C().igemm_plan_fwd(ta, tb, g, bn, True))
-  return Plan(handles, (dy, w, dx, bias), "dgrad {}x{} s{} {}->{} @{}x{}".format(
+  return Plan(handles, (dy, w, dx, bias, stats), "dgrad {}x{} s{} {}->{} @{}x{}".format(
       R, S, stride, Cout, Cin, H, W))
 
 

@@ -368,10 +368,112 @@ def mnist_small():
   for s in (1, 2):
     OH = (9 - 1) // s + 1
     yd = torch.empty(2, OH, OH, 32, device="cuda", dtype=torch.bfloat16)
-    K.depthwise3x3_fwd(xd, wd, yd, s)
+    K.depthwise3x3_fwd(xd, wd, None, yd, s, 0)
     refd = F.conv2d(xd.float().permute(0, 3, 1, 2), wd.float().t().reshape(32, 1, 3, 3), stride=s,
                     padding=1, groups=32).permute(0, 2, 3, 1)
     ok &= _report("depthwise3x3 s{}".format(s), _rel(yd, refd), 2e-2)
+  return ok
+
+
+@check
+def conv_transpose_pixel_loss():
+  import torch
+  import torch.nn.functional as F
+  from tensorflowonspark_b200 import ops
+  from tensorflowonspark_b200.ops import igemm
+  ok = True
+  for (N, h, Ci, Co) in [(2, 8, 64, 128), (2, 16, 320, 64), (3, 4, 64, 8)]:
+    x = torch.randn(N, h, h, Ci, device="cuda").bfloat16()
+    w = (torch.randn(Ci, 3, 3, Co, device="cuda") * 0.1).bfloat16()   # [Cin_T, R, S, Cout_T]
+    y = torch.zeros(N, 2 * h, 2 * h, Co, device="cuda", dtype=torch.bfloat16)
+    s, ss = torch.zeros(Co, device="cuda"), torch.zeros(Co, device="cuda")
+    igemm.conv_dgrad(x, w, y, 2, 1, stats=(s, ss)).run()
+    torch.cuda.synchronize()
+    wt = w.float().permute(0, 3, 1, 2)  # conv_transpose2d weight: [Cin, Cout, kh, kw]
+    ref = F.conv_transpose2d(x.float().permute(0, 3, 1, 2), wt, stride=2, padding=1,
+                             output_padding=1).permute(0, 2, 3, 1)
+    ok &= _report("convT fwd {}".format((N, h, Ci, Co)), _rel(y, ref), 2e-2)
+    ok &= _report("convT fused stats", _rel(s, y.float().sum((0, 1, 2))), 2e-3)
+    # backward pieces: input gradient = stride-2 fprop, weight gradient = stride-2 wgrad
+    g = torch.randn_like(y)
+    xr = x.float().requires_grad_(True)
+    wr = w.float().requires_grad_(True)
+    F.conv_transpose2d(xr.permute(0, 3, 1, 2), wr.permute(0, 3, 1, 2), stride=2, padding=1,
+                       output_padding=1).backward(g.float().permute(0, 3, 1, 2))
+    gx = torch.zeros_like(x)
+    igemm.conv_fprop(g, w, gx, 2, 1).run()
+    gw = torch.zeros(Ci, 3, 3, Co, device="cuda")
+    igemm.conv_wgrad(x, g, gw, 2, 1).run()
+    torch.cuda.synchronize()
+    ok &= _report("convT input grad", _rel(gx, xr.grad), 3e-2)
+    ok &= _report("convT weight grad", _rel(gw, wr.grad), 2e-3)
+  P, V = 5000, 3
+  logits = torch.zeros(P, 8, device="cuda")
+  logits[:, :V] = torch.randn(P, V, device="cuda") * 2
+  lb = logits.bfloat16()
+  labels = torch.randint(0, V, (P,), device="cuda", dtype=torch.int32)
+  dl = torch.empty(P, 8, device="cuda", dtype=torch.bfloat16)
+  loss, corr = torch.zeros(1, device="cuda"), torch.zeros(1, device="cuda")
+  ops.K.pixel_xent(lb, labels, dl, loss, corr, V, 1.0 / P)
+  lr = lb.float()[:, :V].clone().requires_grad_(True)
+  lref = F.cross_entropy(lr, labels.long())
+  lref.backward()
+  ok &= _report("pixel_xent loss", _rel(loss, lref.detach().view(1)), 1e-4)
+  ok &= _report("pixel_xent grad", _rel(dl[:, :V], lr.grad), 1e-2)
+  ok &= _report("pixel_xent pad grad", float(dl[:, V:].float().abs().max()), 1e-12)
+  a = torch.randn(100, 64, device="cuda").bfloat16()
+  cat = torch.zeros(100, 160, device="cuda", dtype=torch.bfloat16)
+  ops.K.copy_channels(a, cat, 64, 0, 96)
+  back = torch.zeros_like(a)
+  ops.K.copy_channels(cat, back, 64, 96, 0)
+  ok &= _report("copy_channels", _rel(back, a) + float(cat[:, :96].float().abs().max()), 1e-12)
+  return ok
+
+
+@check
+def mnist_train():
+  import torch
+  import torch.nn.functional as F
+  from tensorflowonspark_b200.models import mnist
+  torch.manual_seed(0)
+  ref = mnist.MnistCNN().cuda()
+  net = mnist.MnistTrainer(batch=64, lr=0.05)
+  net.load_reference(ref)
+  opt = torch.optim.SGD(ref.parameters(), lr=0.05)
+  templates = (torch.rand(10, 28, 28, device="cuda") > 0.75).float()
+  l_native, l_ref = [], []
+  for step in range(30):
+    y = torch.randint(0, 10, (64,), device="cuda")
+    x = (templates[y] * 0.8 + torch.rand(64, 28, 28, device="cuda") * 0.25).clamp(0, 1)
+    l_native.append(float(net.train_step(x, y.int())))
+    loss = F.cross_entropy(ref(x), y)
+    opt.zero_grad()
+    loss.backward()
+    opt.step()
+    l_ref.append(float(loss))
+  print("mnist native:", " ".join("%.3f" % v for v in l_native[::3]))
+  print("mnist torch :", " ".join("%.3f" % v for v in l_ref[::3]))
+  ok = _report("mnist first-step loss parity", abs(l_native[0] - l_ref[0]) / l_ref[0], 2e-2)
+  ok &= _report("mnist loss curve parity (mean rel diff)",
+                sum(abs(a - b) / max(b, 1e-3) for a, b in zip(l_native, l_ref)) / 30, 0.15)
+  ok &= l_native[-1] < 0.5 * l_native[0]
+  return ok
+
+
+@check
+def unet_step():
+  import torch
+  from tensorflowonspark_b200.models import unet
+  net = unet.UNetTrainer(batch=4, image=128, classes=3, lr=2e-3)
+  x, y = net.synthetic_batch()
+  y = (x[..., 0] > 127).int() + (x[..., 1] > 200).int()  # learnable per-pixel labels
+  losses = []
+  for i in range(25):
+    net.train_step(x, y)
+    losses.append(float(net.loss_sum))
+  print("unet b4 128px losses:", " ".join("%.3f" % l for l in losses[::2]))
+  ok = all(l == l for l in losses) and losses[-1] < 0.8 * losses[0]
+  print("CHECK unet_step {} -> {} {}".format(losses[0], losses[-1], "OK" if ok else "FAIL"))
   return ok
 
 
