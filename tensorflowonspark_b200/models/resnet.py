@@ -264,6 +264,119 @@ class ResNetTrainer(object):
     self.optim.set_lr(lr)
 
 
+class CifarResNetTrainer(object):
+  """ResNet-20/32/56 for 32x32 inputs (basic blocks, 16/32/64 channels) - the network the
+  reference example actually trains (examples/resnet/resnet_cifar_dist.py:208, ``resnet56``,
+  momentum SGD, batch 128, weight decay 2e-4)."""
+
+  def __init__(self, depth=56, batch=128, num_classes=10, device="cuda:0", lr=0.1, momentum=0.9,
+               weight_decay=2e-4, comm=None, seed=1234):
+    assert (depth - 2) % 6 == 0
+    n = (depth - 2) // 6
+    self.device = dev = torch.device(device)
+    self.B, self.image, self.num_classes = batch, 32, num_classes
+    self.VP = (num_classes + 7) // 8 * 8
+    B = batch
+    st = self.store = ParamStore()
+    self.stem = _Unit(st, "stem", 8, 16, 3, 1)
+    self.blocks = []
+    cin = 16
+    for si, width in enumerate((16, 32, 64)):
+      for bi in range(n):
+        stride = 2 if (bi == 0 and si > 0) else 1
+        b = _Block()
+        name = "stage{}.{}".format(si + 1, bi)
+        b.u1 = _Unit(st, name + ".u1", cin, width, 3, stride)
+        b.u2 = _Unit(st, name + ".u2", width, width, 3, 1, zero_gamma=True)
+        b.ds = _Unit(st, name + ".ds", cin, width, 1, stride) if stride != 1 else None
+        b.stride, b.width = stride, width
+        self.blocks.append(b)
+        cin = width
+    self.fc = Dense(st, "fc", 64, self.VP, bias=True, init=normal(0.01))
+    st.finalize(dev, alloc=comm.alloc if comm is not None else None, seed=seed)
+
+    self.in_u8 = _buf((B, 32, 32, 3), dev, torch.uint8)
+    self.x8 = _buf((B, 32, 32, 8), dev)
+    self.labels = torch.zeros(B, dtype=torch.int32, device=dev)
+    self.stem_raw, self.stem_act = _buf((B, 32, 32, 16), dev), _buf((B, 32, 32, 16), dev)
+    self.g_stem_raw = _buf((B, 32, 32, 16), dev)
+    self.stem.bn.build(dev)
+    gx = _buf((B, 32, 32, 16), dev)
+    self.g_stem_act = gx
+    self.stem.conv.build(self.x8, self.stem_raw, self.g_stem_raw, None, stats=self.stem.bn.stats,
+                         need_dgrad=False)
+    x, H = self.stem_act, 32
+    for b in self.blocks:
+      H2, w = (H - 1) // b.stride + 1, b.width
+      b.x = x
+      b.r1, b.a1 = _buf((B, H2, H2, w), dev), _buf((B, H2, H2, w), dev)
+      b.r2, b.out = _buf((B, H2, H2, w), dev), _buf((B, H2, H2, w), dev)
+      b.g_r1, b.g_a1, b.g_r2 = _buf(b.r1.shape, dev), _buf(b.a1.shape, dev), _buf(b.r2.shape, dev)
+      b.g_out = _buf(b.out.shape, dev) if b.ds is not None else gx
+      b.g_x = gx
+      for u in (b.u1, b.u2) + ((b.ds,) if b.ds else ()):
+        u.bn.build(dev)
+      ident = b.ds is None
+      b.u1.conv.build(x, b.r1, b.g_r1, b.g_x, stats=b.u1.bn.stats, dx_accumulate=ident)
+      b.u2.conv.build(b.a1, b.r2, b.g_r2, b.g_a1, stats=b.u2.bn.stats)
+      if b.ds is not None:
+        b.rd, b.idn, b.g_rd = _buf(b.r2.shape, dev), _buf(b.r2.shape, dev), _buf(b.r2.shape, dev)
+        b.ds.conv.build(x, b.rd, b.g_rd, b.g_x, stats=b.ds.bn.stats, dx_accumulate=True)
+      x, H, gx = b.out, H2, b.g_out
+    self.last, self.g_last = x, gx
+    self.avg, self.g_avg = _buf((B, 64), dev), _buf((B, 64), dev)
+    self.logits = _buf((B, self.VP), dev, torch.float32)
+    self.dlogits = _buf((B, self.VP), dev)
+    self.loss_sum = torch.zeros(1, dtype=torch.float32, device=dev)
+    self.correct = torch.zeros(1, dtype=torch.float32, device=dev)
+    self.fc.build(self.avg, self.logits, self.dlogits, self.g_avg)
+    from ..parallel.fused_optim import FusedOptimizer
+    self.optim = FusedOptimizer(st, comm=comm, opt="momentum", lr=lr, momentum=momentum,
+                                weight_decay=weight_decay)
+    self.graph = None
+    self.mean, self.std = [0.4914, 0.4822, 0.4465], [0.2470, 0.2435, 0.2616]
+
+  synthetic_batch = ResNetTrainer.synthetic_batch
+  set_input = ResNetTrainer.set_input
+  capture = ResNetTrainer.capture
+  train_step = ResNetTrainer.train_step
+  set_lr = ResNetTrainer.set_lr
+
+  def step_kernels(self):
+    K = ops.K
+    K.decode_normalize(self.in_u8, self.x8, 0, self.mean, self.std)
+    self.stem.conv.forward()
+    self.stem.bn.forward(self.stem_raw, self.stem_act, None, 1, True)
+    for b in self.blocks:
+      b.u1.conv.forward()
+      b.u1.bn.forward(b.r1, b.a1, None, 1, True)
+      b.u2.conv.forward()
+      if b.ds is not None:
+        b.ds.conv.forward()
+        b.ds.bn.forward(b.rd, b.idn, None, 0, True)
+      b.u2.bn.forward(b.r2, b.out, b.idn if b.ds is not None else b.x, 1, True)
+    K.avgpool_fwd(self.last, self.avg)
+    self.fc.forward()
+    self.loss_sum.zero_()
+    self.correct.zero_()
+    K.softmax_xent(self.logits, self.labels, self.dlogits, self.loss_sum, self.correct,
+                   self.num_classes, 1.0 / self.B)
+    self.optim.zero_grads()
+    self.fc.backward()
+    K.avgpool_bwd(self.g_avg, self.g_last)
+    for b in reversed(self.blocks):
+      b.u2.bn.backward(b.g_out, b.r2, b.out, b.g_r2, dres=b.g_out, relu=True)
+      b.u2.conv.backward()
+      b.u1.bn.backward(b.g_a1, b.r1, b.a1, b.g_r1, relu=True)
+      b.u1.conv.backward()
+      if b.ds is not None:
+        b.ds.bn.backward(b.g_out, b.rd, None, b.g_rd, relu=False)
+        b.ds.conv.backward()
+    self.stem.bn.backward(self.g_stem_act, self.stem_raw, self.stem_act, self.g_stem_raw, relu=True)
+    self.stem.conv.backward()
+    self.optim.step()
+
+
 def piecewise_lr(epoch, batch_size, base=0.1, boundaries=(91, 136, 182), factors=(0.1, 0.01, 0.001)):
   """LR schedule of the reference ResNet example (resnet_cifar_dist.py:35-66):
   0.1 * bs/128, multiplied by 0.1 / 0.01 / 0.001 from epochs 91 / 136 / 182."""

@@ -478,6 +478,22 @@ def unet_step():
 
 
 @check
+def cifar_resnet_step():
+  import torch
+  from tensorflowonspark_b200.models import resnet
+  net = resnet.CifarResNetTrainer(depth=20, batch=32, lr=0.1, weight_decay=0.0)
+  x, y = net.synthetic_batch()
+  losses = []
+  for i in range(60):
+    net.train_step(x, y)
+    losses.append(float(net.loss_sum))
+  print("cifar resnet20 b32 losses:", " ".join("%.3f" % l for l in losses[::4]))
+  ok = all(l == l for l in losses) and losses[-1] < 0.5 * losses[0]
+  print("CHECK cifar_resnet_step {} -> {} {}".format(losses[0], losses[-1], "OK" if ok else "FAIL"))
+  return ok
+
+
+@check
 def resnet_step():
   import torch
   from tensorflowonspark_b200.models import resnet
