@@ -1,0 +1,116 @@
+"""Image segmentation U-Net on Spark executors.
+
+Reference: examples/segmentation/segmentation_spark.py:25-193 (MobileNetV2-encoder U-Net,
+128x128x3 inputs, 3 classes, batch 64, Adam, InputMode.TENSORFLOW with tfds).  Both feeding modes
+are provided here: ``--input_mode tf`` (each worker synthesises / reads its own data) and
+``--input_mode spark`` (BASELINE.json config #4: the images travel RDD -> shared-memory pinned
+ring -> ``cudaMemcpyAsync`` on a copy stream -> device, through ``TFNode.DataFeed``).
+
+  python examples/segmentation/segmentation_spark.py --cluster_size 8 --batch_size 64 --steps 100
+"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+
+IMG = 128
+
+
+def synth_rows(n, seed):
+  """Synthetic oxford-pets-like rows: (uint8 image bytes as a list, uint8 mask as a list)."""
+  import numpy as np
+  rng = np.random.RandomState(seed)
+  rows = []
+  for _ in range(n):
+    img = rng.randint(0, 256, size=(IMG, IMG, 3), dtype=np.uint8)
+    mask = ((img[..., 0] > 127).astype(np.uint8) + (img[..., 1] > 200).astype(np.uint8))
+    rows.append((img.reshape(-1).tolist(), mask.reshape(-1).tolist()))
+  return rows
+
+
+def main_fun(args, ctx):
+  import time
+  import numpy as np
+  import torch
+  from tensorflowonspark_b200.feed import DevicePrefetcher
+  from tensorflowonspark_b200.models import unet
+  torch.cuda.set_device(0)
+  comm = ctx.symmetric_comm() if ctx.world_size > 1 else None
+  B = args.batch_size
+  net = unet.UNetTrainer(batch=B, image=IMG, classes=3, device="cuda:0", lr=args.learning_rate,
+                         comm=comm)
+  if comm is not None:
+    comm.broadcast("weights", root=0)
+    comm.broadcast("aux32", root=0)
+  t0, seen = time.time(), 0
+  if args.input_mode == "spark":
+    feed = ctx.get_data_feed(train_mode=True)
+    pre = DevicePrefetcher([((B, IMG, IMG, 3), torch.uint8), ((B, IMG, IMG), torch.int32)], "cuda:0")
+    hx = [torch.empty(B, IMG, IMG, 3, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    hy = [torch.empty(B, IMG, IMG, dtype=torch.int32).pin_memory() for _ in range(2)]
+    steps = int(args.num_examples * args.epochs * 0.9 / (B * ctx.num_workers))
+    for step in range(steps):
+      rows = feed.next_batch(B)
+      if len(rows) < B:
+        break
+      k = step % 2
+      hx[k].copy_(torch.from_numpy(np.asarray([r[0] for r in rows], dtype=np.uint8).reshape(
+          B, IMG, IMG, 3)))
+      hy[k].copy_(torch.from_numpy(np.asarray([r[1] for r in rows], dtype=np.int32).reshape(
+          B, IMG, IMG)))
+      pre.push((hx[k], hy[k]))
+      bx, by = pre.pop()
+      net.set_input(bx, by)
+      pre.release()
+      loss = net.train_step()
+      seen += B
+      if (step + 1) % 10 == 0 and ctx.is_chief:
+        torch.cuda.synchronize()
+        print("step {:4d} loss {:.4f} {:.0f} images/s".format(
+            step + 1, float(loss), seen * ctx.num_workers / (time.time() - t0)))
+    feed.terminate()
+  else:
+    x, y = net.synthetic_batch(seed=ctx.rank)
+    net.set_input(x, (x[..., 0] > 127).int() + (x[..., 1] > 200).int())
+    net.train_step()
+    net.capture()
+    for step in range(args.steps):
+      loss = net.train_step()
+      if (step + 1) % 10 == 0 and ctx.is_chief:
+        torch.cuda.synchronize()
+        print("step {:4d} loss {:.4f} {:.0f} images/s".format(
+            step + 1, float(loss), (step + 1) * B * ctx.world_size / (time.time() - t0)))
+  torch.cuda.synchronize()
+
+
+if __name__ == "__main__":
+  from tensorflowonspark_b200 import TFCluster
+  from tensorflowonspark_b200._spark import SparkConf, SparkContext
+
+  parser = argparse.ArgumentParser()
+  parser.add_argument("--batch_size", type=int, default=64)
+  parser.add_argument("--cluster_size", type=int, default=1)
+  parser.add_argument("--epochs", type=int, default=1)
+  parser.add_argument("--steps", type=int, default=50)
+  parser.add_argument("--learning_rate", type=float, default=1e-3)
+  parser.add_argument("--input_mode", default="tf", choices=["tf", "spark"])
+  parser.add_argument("--num_examples", type=int, default=2048)
+  args = parser.parse_args()
+  conf = SparkConf().setAppName("segmentation_spark") \
+      .set("spark.executor.instances", str(args.cluster_size)) \
+      .set("spark.executor.resource.gpu.amount", "1").set("spark.task.resource.gpu.amount", "1")
+  sc = SparkContext(conf=conf)
+  if args.input_mode == "spark":
+    parts = args.cluster_size * 4
+    per = args.num_examples // parts
+    rdd = sc.parallelize(range(parts), parts).flatMap(lambda i: synth_rows(per, i))
+    cluster = TFCluster.run(sc, main_fun, args, args.cluster_size, num_ps=0,
+                            input_mode=TFCluster.InputMode.SPARK, master_node="chief")
+    cluster.train(rdd, args.epochs)
+    cluster.shutdown(grace_secs=2)
+  else:
+    cluster = TFCluster.run(sc, main_fun, args, args.cluster_size, num_ps=0,
+                            input_mode=TFCluster.InputMode.TENSORFLOW, master_node="chief")
+    cluster.shutdown()
+  sc.stop()
