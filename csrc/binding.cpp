@@ -212,24 +212,28 @@ void bn_apply(const Tensor& x, c10::optional<Tensor> residual, const Tensor& sca
         "bn_apply");
 }
 void bn_bwd_reduce(const Tensor& dy, const Tensor& x, c10::optional<Tensor> y, const Tensor& mean,
-                   const Tensor& invstd, Tensor dgamma, Tensor dbeta, bool relu) {
+                   const Tensor& invstd, Tensor dgamma, Tensor dbeta, int relu,
+                   c10::optional<Tensor> fscale, c10::optional<Tensor> fshift) {
+  TORCH_CHECK(relu != 1 || (y.has_value() && y->defined()), "bn_bwd_reduce: relu=1 needs y");
+  TORCH_CHECK(relu != 2 || (fscale.has_value() && fshift.has_value()), "bn_bwd_reduce: relu=2 needs scale/shift");
   need(dy, torch::kBFloat16, "dy");
   need(x, torch::kBFloat16, "x");
   const int C = x.size(-1);
   check(tfos::bn_bwd_reduce(dy.data_ptr(), x.data_ptr(), optptr(y), mean.data_ptr<float>(),
-                            invstd.data_ptr<float>(), x.numel() / C, C, relu ? 1 : 0,
-                            dgamma.data_ptr<float>(), dbeta.data_ptr<float>(), cur_stream()),
+                            invstd.data_ptr<float>(), optf(fscale), optf(fshift), x.numel() / C, C,
+                            relu, dgamma.data_ptr<float>(), dbeta.data_ptr<float>(), cur_stream()),
         "bn_bwd_reduce");
 }
 void bn_bwd_apply(const Tensor& dy, const Tensor& x, c10::optional<Tensor> y, const Tensor& gamma,
                   const Tensor& mean, const Tensor& invstd, const Tensor& dgamma,
-                  const Tensor& dbeta, Tensor dx, c10::optional<Tensor> dres, bool relu) {
+                  const Tensor& dbeta, Tensor dx, c10::optional<Tensor> dres, int relu,
+                  c10::optional<Tensor> fscale, c10::optional<Tensor> fshift) {
   const int C = x.size(-1);
   check(tfos::bn_bwd_apply(dy.data_ptr(), x.data_ptr(), optptr(y), gamma.data_ptr<float>(),
                            mean.data_ptr<float>(), invstd.data_ptr<float>(),
-                           dgamma.data_ptr<float>(), dbeta.data_ptr<float>(), dx.data_ptr(),
-                           const_cast<void*>(optptr(dres)), x.numel() / C, C, relu ? 1 : 0,
-                           cur_stream()),
+                           dgamma.data_ptr<float>(), dbeta.data_ptr<float>(), optf(fscale),
+                           optf(fshift), dx.data_ptr(), const_cast<void*>(optptr(dres)),
+                           x.numel() / C, C, relu, cur_stream()),
         "bn_bwd_apply");
 }
 void add_act(const Tensor& a, c10::optional<Tensor> b, Tensor out, int act) {

@@ -157,154 +157,7 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
   }
 }
 
-// dgamma = sum g * xhat, dbeta = sum g, with g = dy * [y > 0] when relu.
-// Same decomposition as column_reduce, but the per-channel statistics are hoisted
-// into registers and two rows are in flight per thread (6 x 16-byte loads).
-__global__ void __launch_bounds__(kRedThreads)
-bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
-                     const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
-                     const float* __restrict__ invstd, long long P, int C, int relu, float* dgamma,
-                     float* dbeta) {
-  const int groups = C >> 3;
-  const int cg = groups < kRedThreads ? groups : kRedThreads;
-  const int rl = kRedThreads / cg;
-  const int g_in = threadIdx.x % cg;
-  const int r_in = threadIdx.x / cg;
-  __shared__ float red[2][kRedThreads][8];
-  for (int g0 = blockIdx.y * cg; g0 < groups; g0 += gridDim.y * cg) {
-    const int g = g0 + g_in;
-    float a0[8], a1[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) a0[j] = 0.f, a1[j] = 0.f;
-    if (g < groups && r_in < rl) {
-      const int c = g * 8;
-      float mu[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) mu[j] = mean[c + j];
-      const long long stride = static_cast<long long>(gridDim.x) * rl;
-      long long p = static_cast<long long>(blockIdx.x) * rl + r_in;
-      for (; p + stride < P; p += 2 * stride) {
-        float gA[8], xA[8], yA[8], gB[8], xB[8], yB[8];
-        const long long oA = p * C + c, oB = (p + stride) * C + c;
-        load8(dy + oA, gA);
-        load8(x + oA, xA);
-        load8(dy + oB, gB);
-        load8(x + oB, xB);
-        if (relu) {
-          load8(y + oA, yA);
-          load8(y + oB, yB);
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float ga = (relu && yA[j] <= 0.f) ? 0.f : gA[j];
-          const float gb = (relu && yB[j] <= 0.f) ? 0.f : gB[j];
-          a0[j] += ga * (xA[j] - mu[j]) + gb * (xB[j] - mu[j]);
-          a1[j] += ga + gb;
-        }
-      }
-      for (; p < P; p += stride) {
-        float gA[8], xA[8], yA[8];
-        const long long oA = p * C + c;
-        load8(dy + oA, gA);
-        load8(x + oA, xA);
-        if (relu) load8(y + oA, yA);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float ga = (relu && yA[j] <= 0.f) ? 0.f : gA[j];
-          a0[j] += ga * (xA[j] - mu[j]);
-          a1[j] += ga;
-        }
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) red[0][threadIdx.x][j] = a0[j], red[1][threadIdx.x][j] = a1[j];
-    __syncthreads();
-    if (r_in == 0 && g < groups) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float s0 = 0.f, s1 = 0.f;
-        for (int r = 0; r < rl; ++r) s0 += red[0][r * cg + g_in][j], s1 += red[1][r * cg + g_in][j];
-        atomicAdd(dgamma + g * 8 + j, s0 * invstd[g * 8 + j]);
-        atomicAdd(dbeta + g * 8 + j, s1);
-      }
-    }
-    __syncthreads();
-  }
-}
-
-// dx = gamma*invstd * (g - dbeta/M - xhat*dgamma/M) = A*g + B*x + K with per-channel A, B, K
-// held in registers; optionally also stores the masked g (gradient of the residual branch),
-// which may alias dy.  Two rows in flight per thread.
-__global__ void __launch_bounds__(kRedThreads)
-bn_bwd_apply_kernel(const __nv_bfloat16* dy, const __nv_bfloat16* __restrict__ x,
-                    const __nv_bfloat16* __restrict__ y, const float* __restrict__ gamma,
-                    const float* __restrict__ mean, const float* __restrict__ invstd,
-                    const float* __restrict__ dgamma, const float* __restrict__ dbeta,
-                    __nv_bfloat16* __restrict__ dx, __nv_bfloat16* dres, long long P, int C,
-                    int relu, float inv_count) {
-  const int groups = C >> 3;
-  const int cg = groups < kRedThreads ? groups : kRedThreads;
-  const int rl = kRedThreads / cg;
-  const int g_in = threadIdx.x % cg;
-  const int r_in = threadIdx.x / cg;
-  if (r_in >= rl) return;
-  for (int g0 = blockIdx.y * cg; g0 < groups; g0 += gridDim.y * cg) {
-    const int g = g0 + g_in;
-    if (g >= groups) continue;
-    const int c = g * 8;
-    float cA[8], cB[8], cK[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float is = invstd[c + j];
-      const float a = gamma[c + j] * is;
-      const float b = -a * is * dgamma[c + j] * inv_count;
-      cA[j] = a;
-      cB[j] = b;
-      cK[j] = -a * dbeta[c + j] * inv_count - b * mean[c + j];
-    }
-    const long long stride = static_cast<long long>(gridDim.x) * rl;
-    long long p = static_cast<long long>(blockIdx.x) * rl + r_in;
-    for (; p + stride < P; p += 2 * stride) {
-      float gA[8], xA[8], yA[8], gB[8], xB[8], yB[8], oA8[8], oB8[8];
-      const long long oA = p * C + c, oB = (p + stride) * C + c;
-      load8(dy + oA, gA);
-      load8(x + oA, xA);
-      load8(dy + oB, gB);
-      load8(x + oB, xB);
-      if (relu) {
-        load8(y + oA, yA);
-        load8(y + oB, yB);
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        gA[j] = (relu && yA[j] <= 0.f) ? 0.f : gA[j];
-        gB[j] = (relu && yB[j] <= 0.f) ? 0.f : gB[j];
-        oA8[j] = cA[j] * gA[j] + cB[j] * xA[j] + cK[j];
-        oB8[j] = cA[j] * gB[j] + cB[j] * xB[j] + cK[j];
-      }
-      store8(dx + oA, oA8);
-      store8(dx + oB, oB8);
-      if (dres != nullptr) {
-        store8(dres + oA, gA);
-        store8(dres + oB, gB);
-      }
-    }
-    for (; p < P; p += stride) {
-      float gA[8], xA[8], yA[8], oA8[8];
-      const long long oA = p * C + c;
-      load8(dy + oA, gA);
-      load8(x + oA, xA);
-      if (relu) load8(y + oA, yA);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        gA[j] = (relu && yA[j] <= 0.f) ? 0.f : gA[j];
-        oA8[j] = cA[j] * gA[j] + cB[j] * xA[j] + cK[j];
-      }
-      store8(dx + oA, oA8);
-      if (dres != nullptr) store8(dres + oA, gA);
-    }
-  }
-}
+// (batch-norm backward lives in bn_bwd.cu)
 
 // generic fused elementwise: out = act(a (+ b)); and relu backward
 __global__ void __launch_bounds__(256)
@@ -694,26 +547,6 @@ cudaError_t bn_apply(const void* x, const void* residual, const float* scale, co
       shift, static_cast<__nv_bfloat16*>(y), total8, C, act);
   TFOS_RET();
 }
-cudaError_t bn_bwd_reduce(const void* dy, const void* x, const void* y, const float* mean,
-                          const float* invstd, long long P, int C, int relu, float* dgamma,
-                          float* dbeta, cudaStream_t s) {
-  bn_bwd_reduce_kernel<<<red_grid(P, C), kRedThreads, 0, s>>>(
-      static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x),
-      static_cast<const __nv_bfloat16*>(y), mean, invstd, P, C, relu, dgamma, dbeta);
-  TFOS_RET();
-}
-cudaError_t bn_bwd_apply(const void* dy, const void* x, const void* y, const float* gamma,
-                         const float* mean, const float* invstd, const float* dgamma,
-                         const float* dbeta, void* dx, void* dres, long long P, int C, int relu,
-                         cudaStream_t s) {
-  bn_bwd_apply_kernel<<<red_grid(P, C, 8), kRedThreads, 0, s>>>(
-      static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x),
-      static_cast<const __nv_bfloat16*>(y), gamma, mean, invstd, dgamma, dbeta,
-      static_cast<__nv_bfloat16*>(dx), static_cast<__nv_bfloat16*>(dres), P, C, relu,
-      1.f / static_cast<float>(P));
-  TFOS_RET();
-}
-
 cudaError_t add_act(const void* a, const void* b, void* out, long long n, int act,
                     cudaStream_t s) {
   add_act_kernel<<<grid_for(n / 8, 256, kMaxBlocks), 256, 0, s>>>(

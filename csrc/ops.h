@@ -20,12 +20,13 @@ cudaError_t bn_inference_coeffs(const float* gamma, const float* beta, const flo
 cudaError_t bn_apply(const void* x, const void* residual, const float* scale, const float* shift,
                      void* y, long long P, int C, int act, cudaStream_t s);
 cudaError_t bn_bwd_reduce(const void* dy, const void* x, const void* y, const float* mean,
-                          const float* invstd, long long P, int C, int relu, float* dgamma,
-                          float* dbeta, cudaStream_t s);
+                          const float* invstd, const float* fscale, const float* fshift,
+                          long long P, int C, int relu, float* dgamma, float* dbeta,
+                          cudaStream_t s);
 cudaError_t bn_bwd_apply(const void* dy, const void* x, const void* y, const float* gamma,
                          const float* mean, const float* invstd, const float* dgamma,
-                         const float* dbeta, void* dx, void* dres, long long P, int C, int relu,
-                         cudaStream_t s);
+                         const float* dbeta, const float* fscale, const float* fshift, void* dx,
+                         void* dres, long long P, int C, int relu, cudaStream_t s);
 cudaError_t add_act(const void* a, const void* b, void* out, long long n, int act, cudaStream_t s);
 cudaError_t relu_bwd(const void* dy, const void* y, void* dx, long long n, cudaStream_t s);
 cudaError_t colsum(const void* x, long long P, int C, float* out, cudaStream_t s);

@@ -52,7 +52,7 @@ class ParamStore(object):
     self.order = order
     if alloc is None:
       alloc = lambda name, n, dt: torch.zeros(n, dtype=dt, device=device)  # noqa: E731
-    self.master = torch.zeros(self.total, dtype=torch.float32, device=device)
+    self.master = alloc("master", self.total, torch.float32)  # symmetric too: broadcastable
     self.weights = alloc("weights", self.total, torch.bfloat16)
     self.grads = alloc("grads", self.total, torch.float32)
     # fp32 replica of the non-decayed tail (BN scale/offset are consumed in fp32)
@@ -145,11 +145,14 @@ class BatchNorm(object):
                                 self.scale, self.shift, self.eps)
     ops.K.bn_apply(x_raw, residual, self.scale, self.shift, y, act)
 
-  def backward(self, dy, x_raw, y, dx, dres=None, relu=True):
-    ops.K.bn_bwd_reduce(dy, x_raw, y if relu else None, self.mean, self.invstd, self.dgamma,
-                        self.dbeta, relu)
-    ops.K.bn_bwd_apply(dy, x_raw, y if relu else None, self.gamma, self.mean, self.invstd,
-                       self.dgamma, self.dbeta, dx, dres, relu)
+  def backward(self, dy, x_raw, y, dx, dres=None, relu=True, residual=False):
+    """relu mask: recomputed from x_raw with the forward scale/shift when the unit has no
+    residual input (saves reading y: 2 of 6-8 bytes per element); from the stored y otherwise."""
+    mode = 0 if not relu else (1 if (residual or dres is not None) else 2)
+    ops.K.bn_bwd_reduce(dy, x_raw, y if mode == 1 else None, self.mean, self.invstd, self.dgamma,
+                        self.dbeta, mode, self.scale, self.shift)
+    ops.K.bn_bwd_apply(dy, x_raw, y if mode == 1 else None, self.gamma, self.mean, self.invstd,
+                       self.dgamma, self.dbeta, dx, dres, mode, self.scale, self.shift)
 
 
 class Conv(object):
@@ -174,6 +177,8 @@ class Conv(object):
     bias = st.f32(self.sbias) if self.sbias is not None else None
     self.fwd = igemm.conv_fprop(x, st.w(self.sw), y, self.stride, self.pad, bias=bias, relu=relu,
                                 stats=stats)
+    self._fwd_args = (x, y, bias, relu, stats)
+    self.fwd_remote = None
     self.wgrad = self.dgrad = None
     if training and dy is not None:
       self.wgrad = igemm.conv_wgrad(dy, x, st.g(self.sw), self.stride, self.pad)
@@ -184,6 +189,18 @@ class Conv(object):
 
   def forward(self):
     self.fwd.run()
+
+  def bind_remote_weights(self, flat_weights):
+    """Second forward plan whose B operand (the filter) is fetched by TMA from ``flat_weights`` -
+    a peer-mapped view of ANOTHER rank's bf16 weight buffer - instead of local memory: the
+    startup broadcast fused with the first convolution that consumes the weights."""
+    x, y, bias, relu, stats = self._fwd_args
+    w = self.store._view(flat_weights, self.sw)
+    self.fwd_remote = igemm.conv_fprop(x, w, y, self.stride, self.pad, bias=bias, relu=relu,
+                                       stats=stats)
+
+  def forward_remote(self):
+    self.fwd_remote.run()
 
   def backward(self):
     self.wgrad.run()
@@ -205,6 +222,8 @@ class Dense(object):
     st = self.store
     bias = st.f32(self.sbias) if self.sbias is not None else None
     self.fwd = igemm.gemm(x, st.w(self.sw), y, "nk", bias=bias, relu=relu)
+    self._fwd_args = (x, y, bias, relu)
+    self.fwd_remote = None
     self.wgrad = self.dgrad = None
     self.dy = dy
     if training and dy is not None:
@@ -214,6 +233,14 @@ class Dense(object):
 
   def forward(self):
     self.fwd.run()
+
+  def bind_remote_weights(self, flat_weights):
+    x, y, bias, relu = self._fwd_args
+    self.fwd_remote = igemm.gemm(x, self.store._view(flat_weights, self.sw), y, "nk", bias=bias,
+                                 relu=relu)
+
+  def forward_remote(self):
+    self.fwd_remote.run()
 
   def backward(self):
     self.wgrad.run()

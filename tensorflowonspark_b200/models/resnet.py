@@ -172,27 +172,64 @@ class ResNetTrainer(object):
     if labels is not None:
       self.labels.copy_(labels, non_blocking=True)
 
+  # ------------------------------------------------- broadcast fused with use
+  def bind_broadcast_root(self, root=0):
+    """Prepare the fused startup broadcast: forward plans whose filters are read by TMA
+    straight out of the ROOT rank's weight buffer over NVLink (tile by tile, as the tcgen05
+    main loop consumes them), while `bcast_pull` fills the local copy on a side stream."""
+    comm = self.comm
+    flat = ops.C().tensor_from_ptr(comm.peer_ptrs("weights")[root], [self.store.total], "bf16")
+    self._root_weights = flat
+    self._root = root
+    w_stem = self.store._view(flat, self.stem_w)
+    self.p_stem_remote = igemm.stem_fprop(self.xp, w_stem, self.stem_raw, stats=self.stem_bn.stats)
+    for b in self.blocks:
+      for u in (b.u1, b.u2, b.u3) + ((b.ds,) if b.ds is not None else ()):
+        u.conv.bind_remote_weights(flat)
+    self.fc.bind_remote_weights(flat)
+    self._side = torch.cuda.Stream(device=self.device)
+
+  def first_step_fused_broadcast(self):
+    """First training step after start-up: the root's variables win (reference semantics of
+    entering strategy.scope(), examples/mnist/keras/mnist_spark.py:55-56) without a separate
+    broadcast phase in front of the first forward pass."""
+    comm = self.comm
+    comm.broadcast("aux32", self._root)  # BN scale/offset + biases: tiny, consumed in fp32
+    comm.barrier()                        # root's weights are final and visible
+    main = torch.cuda.current_stream(self.device)
+    self._side.wait_stream(main)
+    with torch.cuda.stream(self._side):
+      comm.broadcast("weights", self._root)     # local copy for the backward pass / later steps
+      comm.broadcast("master", self._root, slot=60)  # fp32 masters restart from the root's values
+    self._forward(True, remote=True)            # forward consumes the root's tiles over NVLink
+    main.wait_stream(self._side)
+    self._loss(True)
+    self._backward()
+    self.optim.step()
+    return self.loss_sum
+
   # --------------------------------------------------------------- forward
-  def _forward(self, training):
+  def _forward(self, training, remote=False):
     K = ops.K
+    run = (lambda c: c.forward_remote()) if remote else (lambda c: c.forward())
     K.decode_normalize(self.in_u8, self.xp, igemm.STEM_PAD, self.mean, self.std)
-    self.p_stem.run()
+    (self.p_stem_remote if remote else self.p_stem).run()
     self.stem_bn.forward(self.stem_raw, self.stem_act, None, 1, training)
     K.maxpool_fwd(self.stem_act, self.pool, self.pool_idx, 3, 2, 1)
     for b in self.blocks:
       for u, raw, act in ((b.u1, b.r1, b.a1), (b.u2, b.r2, b.a2)):
-        u.conv.forward()
+        run(u.conv)
         u.bn.forward(raw, act, None, 1, training)
-      b.u3.conv.forward()
+      run(b.u3.conv)
       if b.ds is not None:
-        b.ds.conv.forward()
+        run(b.ds.conv)
         b.ds.bn.forward(b.rd, b.idn, None, 0, training)
         idn = b.idn
       else:
         idn = b.x
       b.u3.bn.forward(b.r3, b.out, idn, 1, training)
     K.avgpool_fwd(self.last, self.avg)
-    self.fc.forward()
+    run(self.fc)
 
   def _loss(self, with_grad):
     self.loss_sum.zero_()

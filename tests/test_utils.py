@@ -66,3 +66,42 @@ def test_gpu_placement_rules(monkeypatch):
   monkeypatch.setattr(gpu_info, "MAX_RETRIES", 0)
   with pytest.raises(Exception, match="Unable to find 8 free"):
     gpu_info.get_gpus(8, 0)
+
+
+def test_fault_spec_parsing_and_actions():
+  import time
+  from tensorflowonspark_b200.utils import fault
+  assert fault.parse("raise:rank=1:step=5;delay:rank=0:step=2:secs=0.5") == [
+      {"action": "raise", "rank": 1, "step": 5}, {"action": "delay", "rank": 0, "step": 2, "secs": 0.5}]
+  assert fault.maybe_inject(0, 5, "raise:rank=1:step=5") is None
+  with pytest.raises(fault.InjectedFault):
+    fault.maybe_inject(1, 5, "raise:rank=1:step=5")
+  t0 = time.time()
+  fault.maybe_inject(0, 2, "delay:rank=0:step=2:secs=0.2")
+  assert time.time() - t0 >= 0.2
+  assert fault.maybe_inject(0, 1, "drop_feed:rank=0:step=1") == "drop_feed"
+
+
+def test_injected_fault_surfaces_on_driver(sc, monkeypatch):
+  """A rank that dies mid-training must fail the job (never hang): kill and raise variants."""
+  from tensorflowonspark_b200 import TFCluster
+
+  def fn(args, ctx):
+    from tensorflowonspark_b200.utils import fault
+    feed = ctx.get_data_feed()
+    step = 0
+    while not feed.should_stop():
+      feed.next_batch(10)
+      fault.maybe_inject(ctx.executor_id, step, args["spec"])
+      step += 1
+
+  rdd = sc.parallelize(range(400), 4)
+  cluster = TFCluster.run(sc, fn, {"spec": "raise:rank=1:step=3"}, 2, 0,
+                          input_mode=TFCluster.InputMode.SPARK)
+  with pytest.raises(Exception, match="injected fault|Timeout"):
+    cluster.train(rdd, 1, feed_timeout=5)
+    cluster.shutdown(grace_secs=1)
+  try:
+    cluster.shutdown()
+  except Exception:
+    pass

@@ -250,14 +250,26 @@ def batchnorm():
     yr.backward(dy.float())
     dgamma, dbeta = z(), z()
     dx, dres = torch.empty_like(x), torch.empty_like(x)
-    K.bn_bwd_reduce(dy, x, y, mean, invstd, dgamma, dbeta, True)
-    K.bn_bwd_apply(dy, x, y, gamma, mean, invstd, dgamma, dbeta, dx, dres, True)
+    K.bn_bwd_reduce(dy, x, y, mean, invstd, dgamma, dbeta, 1, None, None)
+    K.bn_bwd_apply(dy, x, y, gamma, mean, invstd, dgamma, dbeta, dx, dres, 1, None, None)
     torch.cuda.synchronize()
     ok &= _report("bn dgamma", _rel(dgamma, g32.grad), 2e-2)
     ok &= _report("bn dbeta", _rel(dbeta, b32.grad), 2e-2)
     ok &= _report("bn dx", _rel(dx, xf.grad), 3e-2)
     mask = (yr > 0).float()
     ok &= _report("bn dres", _rel(dres, dy.float() * mask), 2e-2)
+    # no-residual unit: ReLU mask recomputed from x (mode 2) must match the stored-y mask (mode 1)
+    y2 = torch.empty_like(x)
+    K.bn_apply(x, None, scale, shift, y2, 1)
+    d1, b1, d2, b2 = z(), z(), z(), z()
+    dx1, dx2 = torch.empty_like(x), torch.empty_like(x)
+    K.bn_bwd_reduce(dy, x, y2, mean, invstd, d1, b1, 1, None, None)
+    K.bn_bwd_apply(dy, x, y2, gamma, mean, invstd, d1, b1, dx1, None, 1, None, None)
+    K.bn_bwd_reduce(dy, x, None, mean, invstd, d2, b2, 2, scale, shift)
+    K.bn_bwd_apply(dy, x, None, gamma, mean, invstd, d2, b2, dx2, None, 2, scale, shift)
+    torch.cuda.synchronize()
+    ok &= _report("bn mask-recompute dgamma", _rel(d2, d1), 1e-4)
+    ok &= _report("bn mask-recompute dx", _rel(dx2, dx1), 1e-3)
   return ok
 
 

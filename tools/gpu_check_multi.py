@@ -138,6 +138,33 @@ def main():
       dist.all_reduce(t, op=dist.ReduceOp.MAX)
       if rank == 0:
         print("TIMING nccl all_reduce + unfused momentum update (baseline) {:.3f} ms".format(float(t)))
+  # ---- startup broadcast fused with the first forward pass (filters read over NVLink by TMA)
+  from tensorflowonspark_b200.models import resnet
+  comm2 = symm.from_torch_distributed(dev)
+  net = resnet.ResNetTrainer(depth=50, batch=8, image=64, device=dev, comm=comm2, lr=0.0,
+                             weight_decay=0.0)
+  if rank == 0:  # only the root holds the "real" variables
+    net.store.weights.mul_(1.25)
+    net.store.master.mul_(1.25)
+  else:
+    net.store.weights.mul_(0.5)
+  x, y = net.synthetic_batch(seed=7)  # same batch on every rank
+  net.set_input(x, y)
+  net.bind_broadcast_root(0)
+  torch.cuda.synchronize()
+  dist.barrier()
+  net.first_step_fused_broadcast()
+  torch.cuda.synchronize()
+  mine = net.logits.clone()
+  ref_logits = mine.clone()
+  dist.broadcast(ref_logits, 0)
+  report("fused bcast+fwd: logits equal root's", rel(mine, ref_logits), 1e-6)
+  w_ref = net.store.weights.float().clone()
+  dist.broadcast(w_ref, 0)
+  report("fused bcast: local weight copy", rel(net.store.weights, w_ref), 1e-6)
+  m_ref = net.store.master.clone()
+  dist.broadcast(m_ref, 0)
+  report("fused bcast: fp32 masters", rel(net.store.master, m_ref), 1e-6)
   dist.barrier()
   if rank == 0:
     print("MULTI SUMMARY:", "ALL OK" if ok else "FAILURES")
