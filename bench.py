@@ -246,6 +246,18 @@ def main():
            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "ms_per_step": float(t) / args.steps, "last_loss": losses[-1]}
 
+  # exposed (non-overlapped) all-reduce time per step: BASELINE.json's second metric.  Measured
+  # on eager steps (timed events cannot live inside the captured graph), max over ranks.
+  exposed = None
+  if world > 1 and net.optim.overlap:
+    vals = []
+    for _ in range(5):
+      net.step_kernels()
+      vals.append(net.optim.exposed_ms())
+    t = torch.tensor([sum(vals) / len(vals)], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    exposed = float(t)
+
   if rank == 0:
     out = {
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world,
@@ -264,6 +276,8 @@ def main():
     }
     if e2e is not None:
       out["e2e"] = e2e
+    if exposed is not None:
+      out["exposed_allreduce_ms_per_step"] = exposed
     print(json.dumps(out))
   if dist is not None:
     dist.barrier()

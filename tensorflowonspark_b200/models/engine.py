@@ -174,6 +174,8 @@ class Conv(object):
             need_dgrad=True, training=True):
     st = self.store
     self.x, self.y = x, y
+    if not training:
+      stats = None  # inference: running statistics are used, nothing to accumulate
     bias = st.f32(self.sbias) if self.sbias is not None else None
     self.fwd = igemm.conv_fprop(x, st.w(self.sw), y, self.stride, self.pad, bias=bias, relu=relu,
                                 stats=stats)

@@ -65,7 +65,7 @@ class ResNetTrainer(object):
         b.u2 = _Unit(st, name + ".u2", width, width, 3, stride)
         b.u3 = _Unit(st, name + ".u3", width, width * 4, 1, 1, zero_gamma=True)
         b.ds = _Unit(st, name + ".ds", cin, width * 4, 1, stride) if bi == 0 else None
-        b.stride, b.cin, b.width = stride, cin, width
+        b.stride, b.cin, b.width, b.name = stride, cin, width, name
         self.blocks.append(b)
         cin = width * 4
     self.fc = Dense(st, "fc", cin, num_classes, bias=True, init=normal(0.01))
@@ -85,9 +85,9 @@ class ResNetTrainer(object):
     self.pool = _buf((B, PH, PW, 64), dev)
     self.pool_idx = _buf((B, PH, PW, 64), dev, torch.uint8)
     self.stem_bn.build(dev)
-    self.p_stem = igemm.stem_fprop(self.xp, st.w(self.stem_w), self.stem_raw,
-                                   stats=self.stem_bn.stats)
     tr = training
+    self.p_stem = igemm.stem_fprop(self.xp, st.w(self.stem_w), self.stem_raw,
+                                   stats=self.stem_bn.stats if tr else None)
     if tr:
       self.g_stem_act = _buf((B, OH, OW, 64), dev)
       self.g_stem_raw = _buf((B, OH, OW, 64), dev)
@@ -146,11 +146,28 @@ class ResNetTrainer(object):
     self.optim = None
     if tr:
       from ..parallel.fused_optim import FusedOptimizer
+      buckets = self._comm_buckets() if (comm is not None and comm.world > 1) else None
       self.optim = FusedOptimizer(st, comm=comm, opt=optimizer, lr=lr, momentum=momentum,
-                                  weight_decay=weight_decay)
+                                  weight_decay=weight_decay, buckets=buckets)
     self.graph = None
     self.mean = [0.485, 0.456, 0.406]
     self.std = [0.229, 0.224, 0.225]
+
+  def _comm_buckets(self):
+    """Gradient buckets for overlapping the fused all-reduce with backward: (begin, end, tag)
+    where tag is the index of the block after whose backward the range is final ('stem' = end
+    of backward).  layer4+fc hold 2/3 of the parameters and are final a third into backward."""
+    st = self.store
+
+    def first_offset(prefix):
+      return min(s["offset"] for s in st.order if s["decay"] and s["name"].startswith(prefix))
+
+    def first_block(prefix):
+      return next(i for i, b in enumerate(self.blocks) if b.name.startswith(prefix))
+
+    b3, b4 = first_offset("layer3."), first_offset("layer4.")
+    return [(b4, st.decay_end, first_block("layer4.")), (b3, b4, first_block("layer3.")),
+            (0, b3, "stem"), (st.decay_end, st.total, "stem")]
 
   @staticmethod
   def _stem_init(shape, gen):
@@ -205,7 +222,7 @@ class ResNetTrainer(object):
     main.wait_stream(self._side)
     self._loss(True)
     self._backward()
-    self.optim.step()
+    self.optim.finish()
     return self.loss_sum
 
   # --------------------------------------------------------------- forward
@@ -243,7 +260,8 @@ class ResNetTrainer(object):
     self.optim.zero_grads()
     self.fc.backward()
     K.avgpool_bwd(self.g_avg, self.g_last)
-    for b in reversed(self.blocks):
+    for bi in reversed(range(len(self.blocks))):
+      b = self.blocks[bi]
       # out = relu(bn3(r3) + idn): masked gradient goes to both branches
       b.u3.bn.backward(b.g_out, b.r3, b.out, b.g_r3, dres=b.g_out, relu=True)
       b.u3.conv.backward()
@@ -254,6 +272,7 @@ class ResNetTrainer(object):
       if b.ds is not None:
         b.ds.bn.backward(b.g_out, b.rd, None, b.g_rd, relu=False)
         b.ds.conv.backward()  # accumulates into g_x
+      self.optim.launch(bi)   # buckets that became final start their all-reduce now
     K.maxpool_bwd(self.g_pool, self.pool_idx, self.g_stem_act, 3, 2, 1)
     self.stem_bn.backward(self.g_stem_act, self.stem_raw, self.stem_act, self.g_stem_raw,
                           relu=True)
@@ -265,7 +284,7 @@ class ResNetTrainer(object):
     self._forward(True)
     self._loss(True)
     self._backward()
-    self.optim.step()
+    self.optim.finish()
 
   def capture(self):
     """Capture one training step into a CUDA graph (launch-bound inner loop -> one launch)."""

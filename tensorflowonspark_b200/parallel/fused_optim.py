@@ -7,6 +7,13 @@ cluster spec, tensorflowonspark/TFSparkNode.py:373-384) *and* the Keras
 optimizer update that follows it: one kernel per gradient bucket pulls the peer
 shards over NVLink, averages, applies SGD / momentum / Adam to the fp32 master
 shard and stores the new bf16 weights into every rank's weight buffer.
+
+Buckets are contiguous ranges of the flat parameter vector.  A model may pass
+``buckets=[(begin, end, tag), ...]`` and call ``launch(tag)`` from inside its
+backward pass as soon as the gradients of that range are final; the kernels then
+run on a dedicated communication stream, overlapped with the rest of backward,
+and ``finish()`` joins the streams (``exposed_ms()`` reports how long that join
+actually waited).  ``step()`` = everything at once on the current stream.
 """
 import torch
 
@@ -18,32 +25,27 @@ OPTS = {"sgd": 0, "momentum": 1, "adam": 2}
 class FusedOptimizer(object):
 
   def __init__(self, store, comm=None, opt="momentum", lr=0.1, momentum=0.9, weight_decay=0.0,
-               beta1=0.9, beta2=0.999, eps=1e-7, num_buckets=1, grid=None):
+               beta1=0.9, beta2=0.999, eps=1e-7, buckets=None, grid=None):
     self.store, self.comm = store, comm
     self.opt = OPTS[opt]
     dev = store.master.device
+    self.device = dev
     self.world = comm.world if comm is not None else 1
     self.rank = comm.rank if comm is not None else 0
-    self.hyper_host = torch.tensor(
-        [lr, momentum, weight_decay, 1.0 / self.world, beta1, beta2, eps, 0.0],
-        dtype=torch.float32).pin_memory() if torch.cuda.is_available() else None
     self.hyper = torch.tensor([lr, momentum, weight_decay, 1.0 / self.world, beta1, beta2, eps, 0.0],
                               dtype=torch.float32, device=dev)
     self.state1 = torch.zeros_like(store.master) if self.opt != 0 else None
     self.state2 = torch.zeros_like(store.master) if self.opt == 2 else None
     self.step_count = 0
     self.grid = grid or (148 if self.world == 1 else 64)
-    # contiguous buckets, boundaries on multiples of 8 elements; bucket 0 is launched first
     n = store.total
-    per = (n // num_buckets + 7) // 8 * 8
-    self.buckets = []
-    b = 0
-    while b < n:
-      e = min(n, b + per)
-      self.buckets.append((b, e))
-      b = e
+    if not buckets:
+      buckets = [(0, n, None)]
+    for b, e, _ in buckets:
+      assert b % 8 == 0 and b < e <= n, "bucket bounds must be multiples of 8 inside the vector"
+    self.buckets = list(buckets)
     self._args = []
-    for slot, (b, e) in enumerate(self.buckets):
+    for slot, (b, e, tag) in enumerate(self.buckets):
       d = {
           "master": store.master.data_ptr(),
           "state1": self.state1.data_ptr() if self.state1 is not None else 0,
@@ -66,6 +68,16 @@ class FusedOptimizer(object):
         d["epoch"] = comm.epoch_ptr(slot)
         d["block_counter"] = comm.counter_ptr(slot)
       self._args.append(d)
+    self._by_tag = {}
+    for i, (_, _, tag) in enumerate(self.buckets):
+      self._by_tag.setdefault(tag, []).append(i)
+    self._launched = set()
+    self.overlap = len(self.buckets) > 1 and dev.type == "cuda"
+    if self.overlap:
+      self.comm_stream = torch.cuda.Stream(device=dev)
+      self._ev_ready = [torch.cuda.Event() for _ in self.buckets]
+      self._ev_wait0 = torch.cuda.Event(enable_timing=True)
+      self._ev_wait1 = torch.cuda.Event(enable_timing=True)
 
   def set_lr(self, lr):
     self.hyper[0:1].fill_(float(lr))
@@ -73,14 +85,59 @@ class FusedOptimizer(object):
   def zero_grads(self):
     self.store.grads.zero_()
     ops.count()
+    self._launched = set()
 
-  def step(self, bucket=None):
-    """Launch the fused kernel for one bucket (or all).  Stream order guarantees the
-    bucket's gradients are complete on this rank; the kernel's own flag barrier
-    covers the peers."""
+  def _bump_step(self):
     if self.opt == 2:
       self.step_count += 1
       self.hyper[7:8].add_(1.0)
+
+  # ---------------------------------------------------------------- overlap
+  def launch(self, tag):
+    """Gradients of every bucket tagged ``tag`` are final on the current stream: run their
+    fused all-reduce + update on the communication stream now."""
+    if not self.overlap:
+      return
+    if not self._launched:
+      self._bump_step()
+    main = torch.cuda.current_stream(self.device)
+    for i in self._by_tag.get(tag, []):
+      if i in self._launched:
+        continue
+      self._ev_ready[i].record(main)
+      self.comm_stream.wait_event(self._ev_ready[i])
+      with torch.cuda.stream(self.comm_stream):
+        ops.K.allreduce_opt(self._args[i])
+      self._launched.add(i)
+
+  def finish(self):
+    """Launch whatever has not been launched and make the current stream wait for all of it."""
+    if not self.overlap:
+      return self.step()
+    for tag in list(self._by_tag):
+      self.launch(tag)
+    main = torch.cuda.current_stream(self.device)
+    timing = not torch.cuda.is_current_stream_capturing()  # timed events cannot be captured
+    if timing:
+      self._ev_wait0.record(main)
+    main.wait_stream(self.comm_stream)
+    if timing:
+      self._ev_wait1.record(main)
+    self._timed = timing
+
+  def exposed_ms(self):
+    """Device time the compute stream spent waiting for the communication stream in the last
+    ``finish()`` - the non-overlapped part of the all-reduce (0 when fully hidden)."""
+    if not self.overlap or not getattr(self, "_timed", False):
+      return None
+    self._ev_wait1.synchronize()
+    return self._ev_wait0.elapsed_time(self._ev_wait1)
+
+  # ------------------------------------------------------------ everything
+  def step(self, bucket=None):
+    """Launch the fused kernel for one bucket (or all) on the current stream.  Stream order
+    guarantees this rank's gradients are complete; the kernel's flag barrier covers the peers."""
+    self._bump_step()
     todo = range(len(self.buckets)) if bucket is None else [bucket]
     for i in todo:
       ops.K.allreduce_opt(self._args[i])
