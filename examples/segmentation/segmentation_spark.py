@@ -18,14 +18,16 @@ IMG = 128
 
 
 def synth_rows(n, seed):
-  """Synthetic oxford-pets-like rows: (uint8 image bytes as a list, uint8 mask as a list)."""
+  """Synthetic oxford-pets-like rows: (uint8 image [128,128,3], uint8 mask [128,128]) as numpy
+  arrays - the feeder packs them column-wise into the shared-memory ring without touching
+  individual pixels in Python."""
   import numpy as np
   rng = np.random.RandomState(seed)
   rows = []
   for _ in range(n):
     img = rng.randint(0, 256, size=(IMG, IMG, 3), dtype=np.uint8)
     mask = ((img[..., 0] > 127).astype(np.uint8) + (img[..., 1] > 200).astype(np.uint8))
-    rows.append((img.reshape(-1).tolist(), mask.reshape(-1).tolist()))
+    rows.append((img, mask))
   return rows
 
 
@@ -51,14 +53,12 @@ def main_fun(args, ctx):
     hy = [torch.empty(B, IMG, IMG, dtype=torch.int32).pin_memory() for _ in range(2)]
     steps = int(args.num_examples * args.epochs * 0.9 / (B * ctx.num_workers))
     for step in range(steps):
-      rows = feed.next_batch(B)
-      if len(rows) < B:
+      cols = feed.next_batch_arrays(B)   # [images uint8 [B,128,128,3], masks uint8 [B,128,128]]
+      if not cols or len(cols[0]) < B:
         break
       k = step % 2
-      hx[k].copy_(torch.from_numpy(np.asarray([r[0] for r in rows], dtype=np.uint8).reshape(
-          B, IMG, IMG, 3)))
-      hy[k].copy_(torch.from_numpy(np.asarray([r[1] for r in rows], dtype=np.int32).reshape(
-          B, IMG, IMG)))
+      hx[k].copy_(torch.from_numpy(cols[0]))                       # into page-locked staging
+      hy[k].copy_(torch.from_numpy(cols[1].astype(np.int32)))
       pre.push((hx[k], hy[k]))
       bx, by = pre.pop()
       net.set_input(bx, by)

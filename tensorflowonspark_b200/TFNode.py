@@ -147,7 +147,7 @@ class DataFeed(object):
     self.input_tensors = [t for _, t in sorted(input_mapping.items())] if input_mapping else None
     self.queue_in = mgr.get_queue(qname_in)
     self.queue_out = mgr.get_queue(qname_out) if not train_mode else None
-    self._rows = []        # rows of the block currently being drained
+    self._block, self._off = None, 0   # block currently being drained
     self._ring = None
     self._prefetch = None
 
@@ -162,16 +162,20 @@ class DataFeed(object):
     return self._ring
 
   def _expand(self, item):
-    """Turn one queue item into a list of rows.  Returns None for control markers."""
+    """Turn one queue item into a block: ('rows', list) or ('cols', [ndarray per column], tupled).
+
+    Ring blocks are copied out of the shared slot column-wise (one memcpy per column) and the
+    slot is released immediately, so feeders never wait on a slow consumer of python rows."""
     if isinstance(item, marker.RingBlock):
       ring = self._attach_ring()
       from . import shmring
-      rows = shmring.unpack_rows(ring, item)
+      cols = [c.copy() for c in shmring.unpack_columns(ring, item)]
       ring.release_read(item.pos)
-      return rows
+      tupled = not (len(item.layout) == 1 and len(item.layout[0]) == 5)
+      return ("cols", cols, tupled, item.nrows)
     if isinstance(item, marker.Rows):
-      return item.rows
-    return [item]
+      return ("rows", item.rows, True, len(item.rows))
+    return ("rows", [item], True, 1)
 
   def _pull(self):
     """One blocking queue read.  Returns 'eof', 'end_partition' or 'rows'."""
@@ -184,18 +188,41 @@ class DataFeed(object):
     if isinstance(item, marker.EndPartition):
       self.queue_in.task_done()
       return "end_partition"
-    self._rows = self._expand(item)
-    self._rows.reverse()  # pop() from the end, preserving order
+    self._block, self._off = self._expand(item), 0
     self.queue_in.task_done()
     return "rows"
 
-  # ------------------------------------------------------------------- API
-  def next_batch(self, batch_size):
-    """Up to ``batch_size`` rows (fewer at end of feed / end of an inference partition)."""
-    tensors = [] if self.input_tensors is None else {t: [] for t in self.input_tensors}
-    count = 0
+  def _remaining(self):
+    return 0 if self._block is None else self._block[3] - self._off
+
+  def _take_rows(self, k):
+    kind, data, tupled, _ = self._block
+    lo, hi = self._off, self._off + k
+    self._off = hi
+    if kind == "rows":
+      return data[lo:hi]
+    if not tupled:
+      return data[0][lo:hi].tolist()
+    lists = [c[lo:hi].tolist() for c in data]
+    return [list(r) for r in zip(*lists)]
+
+  def _take_arrays(self, k):
+    import numpy as np
+    kind, data, tupled, _ = self._block
+    lo, hi = self._off, self._off + k
+    self._off = hi
+    if kind == "cols":
+      return [c[lo:hi] for c in data]
+    rows = data[lo:hi]
+    if rows and isinstance(rows[0], (list, tuple)):
+      return [np.asarray([r[c] for r in rows]) for c in range(len(rows[0]))]
+    return [np.asarray(rows)]
+
+  def _fill(self, batch_size, take):
+    """Common batching loop: ``take(k)`` pops k rows of the current block."""
+    parts, count = [], 0
     while count < batch_size:
-      if not self._rows:
+      if self._remaining() == 0:
         if self.done_feeding:
           break
         what = self._pull()
@@ -205,19 +232,42 @@ class DataFeed(object):
           if not self.train_mode and count > 0:
             break
           continue
-      while self._rows and count < batch_size:
-        row = self._rows.pop()
-        if self.input_tensors is None:
-          tensors.append(row)
-        else:
-          for i, t in enumerate(self.input_tensors):
-            tensors[t].append(row[i])
-        count += 1
+      k = min(self._remaining(), batch_size - count)
+      parts.append(take(k))
+      count += k
+    return parts
+
+  # ------------------------------------------------------------------- API
+  def next_batch(self, batch_size):
+    """Up to ``batch_size`` rows (fewer at end of feed / end of an inference partition)."""
+    rows = [r for part in self._fill(batch_size, self._take_rows) for r in part]
+    if self.input_tensors is None:
+      return rows
+    tensors = {t: [] for t in self.input_tensors}
+    for row in rows:
+      for i, t in enumerate(self.input_tensors):
+        tensors[t].append(row[i])
     return tensors
+
+  def next_batch_arrays(self, batch_size):
+    """Column-major fast path: a list with one numpy array per column (``[n, ...]`` each), or a
+    dict keyed by tensor name when ``input_mapping`` was given.  Ring blocks are sliced, never
+    expanded into python objects."""
+    import numpy as np
+    parts = self._fill(batch_size, self._take_arrays)
+    if not parts:
+      cols = []
+    else:
+      ncol = len(parts[0])
+      cols = [parts[0][c] if len(parts) == 1 else np.concatenate([p[c] for p in parts])
+              for c in range(ncol)]
+    if self.input_tensors is None:
+      return cols
+    return dict(zip(self.input_tensors, cols))
 
   def should_stop(self):
     """True once the end-of-feed marker has been consumed."""
-    return self.done_feeding and not self._rows
+    return self.done_feeding and self._remaining() == 0
 
   def batch_results(self, results):
     """Return one result per input row of the last batch to Spark (inference mode)."""
@@ -228,7 +278,7 @@ class DataFeed(object):
     """Stop consuming: flag the executor as terminating and drain whatever is still queued."""
     logger.info("terminate() invoked")
     self.mgr.set("state", "terminating")
-    self._rows = []
+    self._block, self._off = None, 0
     dropped = 0
     while True:
       try:
@@ -264,10 +314,9 @@ class DataFeed(object):
     """
     import numpy as np
     import torch
-    batch = self.next_batch(batch_size)
+    batch = self.next_batch_arrays(batch_size)
     if self.input_tensors is None:
-      cols = list(zip(*batch)) if batch and isinstance(batch[0], (list, tuple)) else [batch]
-      names = list(range(len(cols)))
+      names, cols = list(range(len(batch))), batch
     else:
       names = self.input_tensors
       cols = [batch[t] for t in names]

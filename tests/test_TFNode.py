@@ -94,3 +94,24 @@ def test_terminate_drains_queue():
   q.join()  # every queued item was task_done()'d
   assert orig is tfn._queue_mod.Empty
   mgr.shutdown()
+
+
+def test_next_batch_arrays_from_ring_and_rows():
+  import numpy as np
+  mgr = TFManager.start(b"abc", ["input", "output"], "local")
+  name, ring = shmring.create(4, 1 << 20)
+  mgr.set("ring", {"name": name, "nslots": 4, "slot_bytes": 1 << 20})
+  rows = [(np.full((4, 4, 3), i, np.uint8), np.full((4, 4), i % 3, np.uint8)) for i in range(10)]
+  q = mgr.get_queue("input")
+  q.put(shmring.pack_rows(ring, rows[:6]))
+  q.put(marker.Rows([(r[0].tolist(), r[1].tolist()) for r in rows[6:]]))   # mixed transports
+  q.put(None)
+  feed = TFNode.DataFeed(mgr)
+  a = feed.next_batch_arrays(4)
+  assert a[0].shape == (4, 4, 4, 3) and a[0].dtype == np.uint8 and a[1].shape == (4, 4, 4)
+  a2 = feed.next_batch_arrays(4)          # spans the ring block and the python-rows chunk
+  assert a2[0].shape == (4, 4, 4, 3)
+  assert [int(x[0, 0, 0]) for x in a[0]] + [int(x[0, 0, 0]) for x in a2[0]] == list(range(8))
+  b = feed.next_batch_arrays(8)
+  assert b[0].shape[0] == 2 and int(b[1][1, 0, 0]) == 9 % 3 and feed.should_stop()
+  mgr.shutdown()
