@@ -23,12 +23,9 @@ def synth_rows(n, seed):
   individual pixels in Python."""
   import numpy as np
   rng = np.random.RandomState(seed)
-  rows = []
-  for _ in range(n):
-    img = rng.randint(0, 256, size=(IMG, IMG, 3), dtype=np.uint8)
-    mask = ((img[..., 0] > 127).astype(np.uint8) + (img[..., 1] > 200).astype(np.uint8))
-    rows.append((img, mask))
-  return rows
+  imgs = rng.randint(0, 256, size=(n, IMG, IMG, 3), dtype=np.uint8)      # one vectorised draw
+  masks = (imgs[..., 0] > 127).astype(np.uint8) + (imgs[..., 1] > 200).astype(np.uint8)
+  return [(imgs[i], masks[i]) for i in range(n)]
 
 
 def main_fun(args, ctx):

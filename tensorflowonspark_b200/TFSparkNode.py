@@ -450,10 +450,15 @@ def _post_chunk(queue, ring, rows):
 
 
 def _feed(queue, ring, iterator):
-  count, chunk = 0, []
+  """Post the partition as chunks: at most FEED_CHUNK rows, and - when a ring is attached - no
+  more rows than fit one ring slot (so big rows such as images never fall back to pickling)."""
+  count, chunk, limit = 0, [], FEED_CHUNK
   for row in iterator:
+    if not chunk and ring is not None and count == 0:
+      from . import shmring
+      limit = max(1, min(FEED_CHUNK, shmring.rows_per_slot(ring, row)))
     chunk.append(row)
-    if len(chunk) >= FEED_CHUNK:
+    if len(chunk) >= limit:
       _post_chunk(queue, ring, chunk)
       count += len(chunk)
       chunk = []

@@ -190,6 +190,18 @@ def _as_columns(rows):
   return [np.ascontiguousarray(arr)], False
 
 
+def rows_per_slot(ring, sample_row):
+  """How many rows shaped like ``sample_row`` fit one ring slot (FEED_CHUNK-sized if unknown)."""
+  try:
+    cols = sample_row if isinstance(sample_row, (list, tuple)) else [sample_row]
+    nbytes = sum(int(np.asarray(c).nbytes) for c in cols)
+    if nbytes <= 0:
+      return 1 << 20
+    return max(1, int((ring.slot_bytes - 64 * (len(cols) + 1)) // (nbytes + 8)))
+  except Exception:
+    return 1 << 20
+
+
 def pack_rows(ring, rows, timeout=600.0):
   """Write a block of rows into the next free slot; returns a RingBlock or None if the rows are
   not uniform numeric data (caller falls back to the queue path)."""
