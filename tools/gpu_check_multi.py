@@ -36,8 +36,9 @@ def main():
     nonlocal ok
     good = err == err and err < tol
     ok &= good
-    if rank == 0:
-      print("CHECK {:40s} err={:.3e} tol={:.1e} {}".format(name, err, tol, "OK" if good else "FAIL"))
+    if rank == 0 or not good:
+      print("CHECK[r{}] {:40s} err={:.3e} tol={:.1e} {}".format(rank, name, err, tol,
+                                                                "OK" if good else "FAIL"), flush=True)
 
   # ---- broadcast + barrier
   n = 1 << 20
@@ -147,7 +148,7 @@ def main():
     net.store.weights.mul_(1.25)
     net.store.master.mul_(1.25)
   else:
-    net.store.weights.mul_(0.5)
+    net.store.weights.zero_()   # a rank that consumed its own copy would produce all-zero logits
   x, y = net.synthetic_batch(seed=7)  # same batch on every rank
   net.set_input(x, y)
   net.bind_broadcast_root(0)
@@ -158,7 +159,9 @@ def main():
   mine = net.logits.clone()
   ref_logits = mine.clone()
   dist.broadcast(ref_logits, 0)
-  report("fused bcast+fwd: logits equal root's", rel(mine, ref_logits), 1e-6)
+  # not bit-equal: batch-norm statistics are accumulated with atomics (order varies per run)
+  report("fused bcast+fwd: logits match root's", rel(mine, ref_logits), 2e-2)
+  report("fused bcast+fwd: logits are non-trivial", 1.0 / (float(mine.abs().max()) + 1e-9), 1e3)
   w_ref = net.store.weights.float().clone()
   dist.broadcast(w_ref, 0)
   report("fused bcast: local weight copy", rel(net.store.weights, w_ref), 1e-6)
@@ -166,6 +169,9 @@ def main():
   dist.broadcast(m_ref, 0)
   report("fused bcast: fp32 masters", rel(net.store.master, m_ref), 1e-6)
   dist.barrier()
+  flag = torch.tensor([1 if ok else 0], device=dev)
+  dist.all_reduce(flag, op=dist.ReduceOp.MIN)   # every rank must have passed every check
+  ok = bool(int(flag))
   if rank == 0:
     print("MULTI SUMMARY:", "ALL OK" if ok else "FAILURES")
   dist.destroy_process_group()
