@@ -12,6 +12,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "ops.h"
 #include "ptx.cuh"
@@ -196,13 +197,20 @@ inline dim3 red_grid(long long P, int C, int waves) {
   return dim3(static_cast<unsigned>(bx), static_cast<unsigned>(gy));
 }
 
+// grid = resident blocks per SM (launch bounds: 2) x 148 SMs x waves; tunable for experiments
+inline int env_waves(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v != nullptr && atoi(v) > 0 ? atoi(v) : dflt;
+}
+
 }  // namespace
 
 cudaError_t bn_bwd_reduce(const void* dy, const void* x, const void* y, const float* mean,
                           const float* invstd, const float* fscale, const float* fshift,
                           long long P, int C, int relu, float* dgamma, float* dbeta,
                           cudaStream_t s) {
-  bn_bwd_reduce_kernel<<<red_grid(P, C, 3), kThreads, 0, s>>>(
+  static const int waves = env_waves("TFOS_BN_WAVES_REDUCE", 2);
+  bn_bwd_reduce_kernel<<<red_grid(P, C, waves), kThreads, 0, s>>>(
       static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x),
       static_cast<const __nv_bfloat16*>(y), mean, invstd, fscale, fshift, P, C, relu, dgamma,
       dbeta);
@@ -213,7 +221,8 @@ cudaError_t bn_bwd_apply(const void* dy, const void* x, const void* y, const flo
                          const float* mean, const float* invstd, const float* dgamma,
                          const float* dbeta, const float* fscale, const float* fshift, void* dx,
                          void* dres, long long P, int C, int relu, cudaStream_t s) {
-  bn_bwd_apply_kernel<<<red_grid(P, C, 6), kThreads, 0, s>>>(
+  static const int waves = env_waves("TFOS_BN_WAVES_APPLY", 2);
+  bn_bwd_apply_kernel<<<red_grid(P, C, waves), kThreads, 0, s>>>(
       static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x),
       static_cast<const __nv_bfloat16*>(y), gamma, mean, invstd, dgamma, dbeta, fscale, fshift,
       static_cast<__nv_bfloat16*>(dx), static_cast<__nv_bfloat16*>(dres), P, C, relu,

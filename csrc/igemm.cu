@@ -58,7 +58,12 @@ __device__ __forceinline__ void red_shared_add(float* p, float v) {
   asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(smem_u32(p)), "f"(v) : "memory");
 }
 
-template <int BN, bool B_MN>
+// EPI selects a compile-time epilogue so the common cases carry no per-element flag tests:
+//   0 plain store, 1 fused BN statistics, 2 read-modify-write accumulate,
+//   4 generic (bias / ReLU / ReLU6 / statistics / accumulate decided at run time).
+constexpr int kEpiPlain = 0, kEpiStats = 1, kEpiAccum = 2, kEpiGeneric = 4;
+
+template <int BN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const FwdArgs a, const int total_tiles) {
@@ -185,7 +190,11 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int q = warp & 3;     // TMEM lane quarter this warp may read
     const int half = ew >> 2;   // which column slabs / chunks this warp takes
     const int et = threadIdx.x - 64;
-    const bool do_stats = a.col_sum != nullptr;
+    constexpr bool kGeneric = (EPI & kEpiGeneric) != 0;
+    const bool do_stats = kGeneric ? (a.col_sum != nullptr) : ((EPI & kEpiStats) != 0);
+    const bool acc_on = kGeneric ? (a.accumulate != 0) : ((EPI & kEpiAccum) != 0);
+    const bool bias_on = kGeneric && a.bias != nullptr;
+    const bool relu_on = kGeneric && a.relu != 0;
     const uint32_t stg = smem_u32(out_stage + ew * 4096);
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -212,7 +221,7 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const bool fast = !a.out_fp32 && (nt * BN + BN <= a.n_valid) && (a.ldo & 7) == 0;
       if (fast) {
         __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(a.out);
-        const bool relu_early = a.relu && !a.accumulate;
+        const bool relu_early = relu_on && !acc_on;
         // per-tile row bookkeeping for the coalesced store phase: lane handles rows
         // i*4 + (lane >> 3), i = 0..7; fetch their offsets / validity once, not per slab
         const uint32_t vmask = __ballot_sync(0xffffffff, valid);
@@ -235,7 +244,7 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 64; j += 2) {
             float f0 = __uint_as_float(v[j]), f1 = __uint_as_float(v[j + 1]);
-            if (a.bias != nullptr) {
+            if (bias_on) {
               f0 += __ldg(a.bias + col0 + j);
               f1 += __ldg(a.bias + col0 + j + 1);
             }
@@ -294,7 +303,7 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const long long roff = roffs[i];
             if ((vmask >> r2) & 1u) {
               __nv_bfloat16* o = obase + roff + c * 64 + sg2 * 8;
-              if (a.accumulate) {
+              if (acc_on) {
                 const uint4 p = *reinterpret_cast<const uint4*>(o);
                 float2 n0 = unpack_bf16x2(val.x), n1 = unpack_bf16x2(val.y),
                        n2 = unpack_bf16x2(val.z), n3 = unpack_bf16x2(val.w);
@@ -302,7 +311,7 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                              p2 = unpack_bf16x2(p.z), p3 = unpack_bf16x2(p.w);
                 n0.x += p0.x, n0.y += p0.y, n1.x += p1.x, n1.y += p1.y;
                 n2.x += p2.x, n2.y += p2.y, n3.x += p3.x, n3.y += p3.y;
-                if (a.relu) {
+                if (relu_on) {
                   n0.x = fmaxf(n0.x, 0.f), n0.y = fmaxf(n0.y, 0.f), n1.x = fmaxf(n1.x, 0.f);
                   n1.y = fmaxf(n1.y, 0.f), n2.x = fmaxf(n2.x, 0.f), n2.y = fmaxf(n2.y, 0.f);
                   n3.x = fmaxf(n3.x, 0.f), n3.y = fmaxf(n3.y, 0.f);
@@ -481,19 +490,36 @@ bool encode(const TmapDesc& d, CUtensorMap* out, char* err, int errlen) {
   return true;
 }
 
-template <int BN, bool B_MN>
-cudaError_t launch_fwd(const IGemmPlan* p, cudaStream_t s) {
+template <int BN, bool B_MN, int EPI>
+cudaError_t launch_fwd_epi(const IGemmPlan* p, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_fwd_kernel<BN, B_MN>,
+    cudaError_t e = cudaFuncSetAttribute(igemm_fwd_kernel<BN, B_MN, EPI>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          FwdCfg<BN>::kSmem);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  igemm_fwd_kernel<BN, B_MN><<<p->grid, kThreads, FwdCfg<BN>::kSmem, s>>>(p->tmA, p->tmB, p->fa,
-                                                                           p->total_work);
+  igemm_fwd_kernel<BN, B_MN, EPI><<<p->grid, kThreads, FwdCfg<BN>::kSmem, s>>>(
+      p->tmA, p->tmB, p->fa, p->total_work);
   return cudaGetLastError();
+}
+
+template <int BN, bool B_MN>
+cudaError_t launch_fwd(const IGemmPlan* p, cudaStream_t s) {
+  const FwdArgs& f = p->fa;
+  const bool ragged = f.out_fp32 || (f.ldo & 7) != 0 || (f.n_valid % BN) != 0;
+  const bool generic = ragged || f.bias != nullptr || f.relu != 0 ||
+                       (f.col_sum != nullptr && f.accumulate);
+  if (generic) return launch_fwd_epi<BN, B_MN, kEpiGeneric>(p, s);
+  if (B_MN) {  // data gradients: plain or accumulate (statistics only through the generic path)
+    if (f.col_sum != nullptr) return launch_fwd_epi<BN, B_MN, kEpiGeneric>(p, s);
+    return f.accumulate ? launch_fwd_epi<BN, B_MN, kEpiAccum>(p, s)
+                        : launch_fwd_epi<BN, B_MN, kEpiPlain>(p, s);
+  }
+  if (f.accumulate) return launch_fwd_epi<BN, B_MN, kEpiGeneric>(p, s);
+  return f.col_sum != nullptr ? launch_fwd_epi<BN, B_MN, kEpiStats>(p, s)
+                              : launch_fwd_epi<BN, B_MN, kEpiPlain>(p, s);
 }
 
 }  // namespace
