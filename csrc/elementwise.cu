@@ -213,10 +213,14 @@ colsum_kernel(const __nv_bfloat16* __restrict__ x, long long P, int C, float* ou
 // ----------------------------------------------------------------- pooling
 // max pool k x k, stride s, pad p over NHWC; records the argmax tap so the
 // backward routes the gradient to exactly one input (PyTorch semantics).
+// K > 0: window known at compile time - the K*K 16-byte loads of a thread are all in flight
+// at once (ResNet's 3x3/2 pool); K == 0: run-time window.
+template <int K, int S, int PAD>
 __global__ void __launch_bounds__(256)
 maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
-                   uint8_t* __restrict__ idx, int N, int H, int W, int C, int OH, int OW, int k,
-                   int s, int pad) {
+                   uint8_t* __restrict__ idx, int N, int H, int W, int C, int OH, int OW, int k_rt,
+                   int s_rt, int pad_rt) {
+  const int k = K > 0 ? K : k_rt, s = K > 0 ? S : s_rt, pad = K > 0 ? PAD : pad_rt;
   const int groups = C >> 3;
   const long long total = static_cast<long long>(N) * OH * OW * groups;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -231,17 +235,40 @@ maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restric
     int bi[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) best[j] = -INFINITY, bi[j] = 0;
-    for (int kh = 0; kh < k; ++kh) {
-      const int h = oh * s - pad + kh;
-      if (h < 0 || h >= H) continue;
-      for (int kw = 0; kw < k; ++kw) {
-        const int w = ow * s - pad + kw;
-        if (w < 0 || w >= W) continue;
-        float f[8];
-        load8(x + ((static_cast<long long>(n) * H + h) * W + w) * C + g * 8, f);
+    if (K > 0) {
+      uint4 raw[K > 0 ? K * K : 1];
+      bool ok[K > 0 ? K * K : 1];
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (f[j] > best[j]) best[j] = f[j], bi[j] = kh * k + kw;
+      for (int t = 0; t < K * K; ++t) {
+        const int h = oh * S - PAD + t / (K > 0 ? K : 1), w = ow * S - PAD + t % (K > 0 ? K : 1);
+        ok[t] = h >= 0 && h < H && w >= 0 && w < W;
+        raw[t] = make_uint4(0u, 0u, 0u, 0u);
+        if (ok[t])
+          raw[t] = ld_nc_v4(x + ((static_cast<long long>(n) * H + h) * W + w) * C + g * 8);
+      }
+#pragma unroll
+      for (int t = 0; t < K * K; ++t) {
+        if (!ok[t]) continue;
+        const uint32_t wd[4] = {raw[t].x, raw[t].y, raw[t].z, raw[t].w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float f = __uint_as_float((j & 1) ? (wd[j >> 1] & 0xffff0000u) : (wd[j >> 1] << 16));
+          if (f > best[j]) best[j] = f, bi[j] = t;
+        }
+      }
+    } else {
+      for (int kh = 0; kh < k; ++kh) {
+        const int h = oh * s - pad + kh;
+        if (h < 0 || h >= H) continue;
+        for (int kw = 0; kw < k; ++kw) {
+          const int w = ow * s - pad + kw;
+          if (w < 0 || w >= W) continue;
+          float f[8];
+          load8(x + ((static_cast<long long>(n) * H + h) * W + w) * C + g * 8, f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (f[j] > best[j]) best[j] = f[j], bi[j] = kh * k + kw;
+        }
       }
     }
     store8(y + i * 8, best);
@@ -288,6 +315,65 @@ maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restri
         }
       }
     store8(dx + i * 8, acc);
+  }
+}
+
+// 3x3 / stride 2 / pad 1: the 2x2 input block (2m..2m+1, 2n..2n+1) is covered by the four
+// windows (m..m+1, n..n+1) only - four (dy, idx) loads produce four dx pixels.
+__global__ void __launch_bounds__(256)
+maxpool_bwd_3x3s2_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx,
+                         __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C, int OH,
+                         int OW) {
+  const int groups = C >> 3;
+  const int BH = (H + 1) >> 1, BW = (W + 1) >> 1;
+  const long long total = static_cast<long long>(N) * BH * BW * groups;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i % groups);
+    long long r = i / groups;
+    const int bw = static_cast<int>(r % BW);
+    r /= BW;
+    const int bh = static_cast<int>(r % BH);
+    const int n = static_cast<int>(r / BH);
+    uint4 gq[4];
+    uint2 iq[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int oh = bh + (t >> 1), ow = bw + (t & 1);
+      gq[t] = make_uint4(0u, 0u, 0u, 0u);
+      iq[t] = make_uint2(0xffffffffu, 0xffffffffu);  // tap 255 never matches
+      if (oh < OH && ow < OW) {
+        const long long o = ((static_cast<long long>(n) * OH + oh) * OW + ow) * C + g * 8;
+        gq[t] = ld_nc_v4(dy + o);
+        iq[t] = *reinterpret_cast<const uint2*>(idx + o);
+      }
+    }
+    // tap (kh*3+kw) through which window t sees pixel (dh, dw) of the block; -1: not covered
+    //   window (m,n):   (0,0)->4 (0,1)->5 (1,0)->7 (1,1)->8
+    //   window (m,n+1): (0,1)->3 (1,1)->6      window (m+1,n): (1,0)->1 (1,1)->2
+    //   window (m+1,n+1): (1,1)->0
+    const int tapmap[4][4] = {{4, -1, -1, -1}, {5, 3, -1, -1}, {7, -1, 1, -1}, {8, 6, 2, 0}};
+#pragma unroll
+    for (int px = 0; px < 4; ++px) {
+      const int h = 2 * bh + (px >> 1), w = 2 * bw + (px & 1);
+      if (h >= H || w >= W) continue;
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int tap = tapmap[px][t];
+        if (tap < 0) continue;
+        const uint32_t wd[4] = {gq[t].x, gq[t].y, gq[t].z, gq[t].w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int tj = ((j < 4 ? iq[t].x : iq[t].y) >> ((j & 3) * 8)) & 0xff;
+          const float f = __uint_as_float((j & 1) ? (wd[j >> 1] & 0xffff0000u) : (wd[j >> 1] << 16));
+          if (tj == tap) acc[j] += f;
+        }
+      }
+      store8(dx + ((static_cast<long long>(n) * H + h) * W + w) * C + g * 8, acc);
+    }
   }
 }
 
@@ -413,13 +499,25 @@ decode_normalize_kernel(const uint8_t* __restrict__ in, __nv_bfloat16* __restric
     const long long nh = i / Wp;
     const int w = wp - wofs;
     __nv_bfloat16* o = out + i * Cp;
-    if (w < 0 || w >= W) {
-      for (int c = 0; c < Cp; ++c) o[c] = __float2bfloat16_rn(0.f);
+    const bool inside = w >= 0 && w < W;
+    const uint8_t* p = in + (nh * W + (inside ? w : 0)) * C;
+    if ((Cp & 7) == 0) {
+      for (int c0 = 0; c0 < Cp; c0 += 8) {  // one 16-byte store per 8 channels
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = c0 + j;
+          v[j] = (inside && c < C)
+                     ? (static_cast<float>(p[c]) * (1.f / 255.f) - mean[c % 3]) * istd[c % 3]
+                     : 0.f;
+        }
+        store8(o + c0, v);
+      }
     } else {
-      const uint8_t* p = in + (nh * W + w) * C;
       for (int c = 0; c < Cp; ++c) {
         float v = 0.f;
-        if (c < C) v = (static_cast<float>(p[c]) * (1.f / 255.f) - mean[c % 3]) * istd[c % 3];
+        if (inside && c < C)
+          v = (static_cast<float>(p[c]) * (1.f / 255.f) - mean[c % 3]) * istd[c % 3];
         o[c] = __float2bfloat16_rn(v);
       }
     }
@@ -568,13 +666,25 @@ cudaError_t colsum(const void* x, long long P, int C, float* out, cudaStream_t s
 cudaError_t maxpool_fwd(const void* x, void* y, uint8_t* idx, int N, int H, int W, int C, int OH,
                         int OW, int k, int stride, int pad, cudaStream_t s) {
   const long long total = static_cast<long long>(N) * OH * OW * (C >> 3);
-  maxpool_fwd_kernel<<<grid_for(total, 256, kMaxBlocks * 4), 256, 0, s>>>(
-      static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), idx, N, H, W, C, OH,
-      OW, k, stride, pad);
+  if (k == 3 && stride == 2 && pad == 1)
+    maxpool_fwd_kernel<3, 2, 1><<<grid_for(total, 256, kMaxBlocks * 4), 256, 0, s>>>(
+        static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), idx, N, H, W, C, OH,
+        OW, k, stride, pad);
+  else
+    maxpool_fwd_kernel<0, 0, 0><<<grid_for(total, 256, kMaxBlocks * 4), 256, 0, s>>>(
+        static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), idx, N, H, W, C, OH,
+        OW, k, stride, pad);
   TFOS_RET();
 }
 cudaError_t maxpool_bwd(const void* dy, const uint8_t* idx, void* dx, int N, int H, int W, int C,
                         int OH, int OW, int k, int stride, int pad, cudaStream_t s) {
+  if (k == 3 && stride == 2 && pad == 1) {
+    const long long blocks = static_cast<long long>(N) * ((H + 1) / 2) * ((W + 1) / 2) * (C >> 3);
+    maxpool_bwd_3x3s2_kernel<<<grid_for(blocks, 256, kMaxBlocks * 4), 256, 0, s>>>(
+        static_cast<const __nv_bfloat16*>(dy), idx, static_cast<__nv_bfloat16*>(dx), N, H, W, C,
+        OH, OW);
+    TFOS_RET();
+  }
   const long long total = static_cast<long long>(N) * H * W * (C >> 3);
   maxpool_bwd_kernel<<<grid_for(total, 256, kMaxBlocks * 4), 256, 0, s>>>(
       static_cast<const __nv_bfloat16*>(dy), idx, static_cast<__nv_bfloat16*>(dx), N, H, W, C, OH,

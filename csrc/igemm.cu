@@ -231,6 +231,18 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int i = 0; i < 8; ++i) roffs[i] = __shfl_sync(0xffffffff, off, i * 4 + (lane >> 3));
 #pragma unroll 1
         for (int c = half; c < BN / 64; c += 2) {
+          // accumulate mode: the previous values do not depend on the MMA - issue all eight
+          // 16-byte loads of this slab now so their latency overlaps the TMEM read + staging
+          uint4 prev[8];
+          if (acc_on) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r2 = i * 4 + (lane >> 3);
+              prev[i] = make_uint4(0u, 0u, 0u, 0u);
+              if ((vmask >> r2) & 1u)
+                prev[i] = *reinterpret_cast<const uint4*>(obase + roffs[i] + c * 64 + (lane & 7) * 8);
+            }
+          }
           uint32_t v[64];
           {
             uint32_t (&lo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
@@ -304,7 +316,7 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if ((vmask >> r2) & 1u) {
               __nv_bfloat16* o = obase + roff + c * 64 + sg2 * 8;
               if (acc_on) {
-                const uint4 p = *reinterpret_cast<const uint4*>(o);
+                const uint4 p = prev[i];
                 float2 n0 = unpack_bf16x2(val.x), n1 = unpack_bf16x2(val.y),
                        n2 = unpack_bf16x2(val.z), n3 = unpack_bf16x2(val.w);
                 const float2 p0 = unpack_bf16x2(p.x), p1 = unpack_bf16x2(p.y),

@@ -13,12 +13,16 @@ These replace the cuDNN/cuBLAS calls the reference reaches through TensorFlow
 (SURVEY.md section 2.6(b)).
 """
 import math
+import os
 
 from .. import _build
 
 BLOCK_M = 128
 BLOCK_K = 64
 _launches = 0
+# weight-gradient tiling knobs (tools/bench_igemm.py sweeps them)
+_WGRAD_WIDE = os.environ.get("TFOS_WGRAD_WIDE", "0") == "1"
+_WGRAD_WORK = int(os.environ.get("TFOS_WGRAD_WORK", "0"))  # 0: per-layer heuristic
 
 
 def launch_count():
@@ -256,6 +260,8 @@ def _wgrad_plan(dy, dy_whn, Cout, x, x_whn, Cin, dw, ldw, taps, mul, es, box=Non
   assert (bw * bh * bnn) % 16 == 0 and bw * bh * bnn <= 128
   n_valid = Cin if n_valid is None else n_valid
   bn = 64 if n_valid <= 64 else 128
+  if n_valid % 256 == 0 and _WGRAD_WIDE:
+    bn = 256  # fewer operand bytes per MMA: 96 instead of 128 B/clk of smem + L2 traffic
   ta = _tmap4(dy, dy_whn, Cout, (bw, bh, bnn))
   if es == 1:
     tb = _tmap4(x, x_whn, Cin, (bw, bh, bnn))
@@ -264,7 +270,15 @@ def _wgrad_plan(dy, dy_whn, Cout, x, x_whn, Cin, dw, ldw, taps, mul, es, box=Non
   m_tiles, n_tiles = -(-Cout // 128), -(-n_valid // bn)
   out_tiles = len(taps) * m_tiles * n_tiles
   total_boxes = tw * th * tn
-  k_splits = max(1, min(-(-296 // out_tiles), max(1, total_boxes // 2)))
+  # split-K work items (measured, tools/bench_igemm.py --kind wgrad): the HBM-bound 1x1 layers
+  # with many pixels want one wave (fewer fp32 atomics), everything else two to four
+  work = _WGRAD_WORK
+  if work == 0:
+    if len(taps) == 1:
+      work = 148 if total_boxes >= 1024 else 592
+    else:
+      work = 592 if Cout <= 64 else 296
+  k_splits = max(1, min(-(-work // out_tiles), max(1, total_boxes // 2)))
   g = {
       "tiles_w": tw, "tiles_h": th, "tiles_n": tn, "box_w": bw, "box_h": bh, "box_n": bnn,
       "mul_w": mul, "mul_h": mul, "num_taps": len(taps),

@@ -36,6 +36,11 @@ CASES = [
     ("l3c2_dgrad", "dgrad", (14, 14, 256, 256, 3, 1)),
     ("l1c2_wgrad", "wgrad", (56, 56, 64, 64, 3, 1)),
     ("l1c3_wgrad", "wgrad", (56, 56, 64, 256, 1, 1)),
+    ("l1c1_wgrad", "wgrad", (56, 56, 256, 64, 1, 1)),
+    ("l2c2_wgrad", "wgrad", (28, 28, 128, 128, 3, 1)),
+    ("l2c3_wgrad", "wgrad", (28, 28, 128, 512, 1, 1)),
+    ("l3c1_wgrad", "wgrad", (14, 14, 1024, 256, 1, 1)),
+    ("l3c3_wgrad", "wgrad", (14, 14, 256, 1024, 1, 1)),
     ("l3c2_wgrad", "wgrad", (14, 14, 256, 256, 3, 1)),
     ("l4c2_wgrad", "wgrad", (7, 7, 512, 512, 3, 1)),
     ("l4c3_wgrad", "wgrad", (7, 7, 512, 2048, 1, 1)),
@@ -78,13 +83,14 @@ def main():
   ap.add_argument("--only", default=None)
   ap.add_argument("--iters", type=int, default=20)
   ap.add_argument("--no-stats", action="store_true")
+  ap.add_argument("--kind", default=None, help="fprop | dgrad | wgrad")
   args = ap.parse_args()
   hbm, tf, src = peaks()
   print("peaks ({}): HBM {:.0f} GB/s, bf16 {:.0f} TFLOP/s".format(src, hbm, tf))
   print("{:12s} {:6s} {:>9s} {:>9s} {:>9s} {:>7s} {:>7s}".format(
       "case", "kind", "us", "TFLOP/s", "GB/s", "%flops", "%hbm"))
   for name, kind, shape in CASES:
-    if args.only and name != args.only:
+    if (args.only and name != args.only) or (args.kind and kind != args.kind):
       continue
     H, W, Ci, Co, k, s = shape
     per = 2.0 * B * (H * W * Ci + H * W * Co)
