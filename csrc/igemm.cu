@@ -24,6 +24,7 @@
 // mbarriers between MMA and epilogue, so the epilogue of tile i overlaps the
 // main loop of tile i+1.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -53,6 +54,12 @@ struct FwdCfg {
   static constexpr int kOutStageBytes = kEpiWarps * 4096;  // per warp: 32 rows x 128 B
   static constexpr int kSmem = kStages * kStage + kStatBytes + kOutStageBytes + 256;
 };
+// Weight-stationary mode: when all K blocks of a CTA's B (filter) tile fit next to >= 4 A stages,
+// B is loaded once per CTA and only A streams - the per-tile L2 traffic of the small-K layers
+// (1x1 convolutions, 64-channel 3x3) drops by the B share (up to 2/3), which matters because
+// those layers are bound by the ~6 KB/clk L2->SM fabric, not by HBM or the tensor pipe.
+constexpr int kMaxStages = 12;
+constexpr int kMinAStages = 4;
 
 __device__ __forceinline__ void red_shared_add(float* p, float v) {
   asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(smem_u32(p)), "f"(v) : "memory");
@@ -73,10 +80,11 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* out_stage = smem + Cfg::kStages * Cfg::kStage + Cfg::kStatBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + Cfg::kOutStageBytes);
   uint64_t* full = bars;
-  uint64_t* empty = bars + Cfg::kStages;
-  uint64_t* tfull = bars + 2 * Cfg::kStages;
+  uint64_t* empty = bars + kMaxStages;
+  uint64_t* tfull = bars + 2 * kMaxStages;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* bfull = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull + 1);
 
   const int warp = __shfl_sync(0xffffffff, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
@@ -88,7 +96,7 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int i = 0; i < Cfg::kStages; ++i) {
+    for (int i = 0; i < kMaxStages; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
@@ -96,6 +104,7 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], kEpiWarps);
     }
+    mbar_init(bfull, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -111,13 +120,36 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int k_iters = a.num_taps * a.k_chunks;
   const int rows = a.box_w * a.box_h * a.box_n;
-  const uint32_t stage_tx = static_cast<uint32_t>(rows) * 128u + Cfg::kBBytes;
+  const bool resident = a.b_resident != 0;
+  const int nstages = resident ? a.a_stages : Cfg::kStages;
+  const uint32_t stage_stride = resident ? kABytes : Cfg::kStage;
+  uint8_t* const ring = smem + (resident ? k_iters * Cfg::kBBytes : 0);  // B region first
+  const uint32_t stage_tx = static_cast<uint32_t>(rows) * 128u + (resident ? 0u : Cfg::kBBytes);
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      auto load_b = [&](uint8_t* sB, uint64_t* bar, int nt, int t, int kc) {
+        if (B_MN) {
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j)
+            tma_load_2d(sB + j * 8192, &tmB, bar, nt * BN + j * 64 + a.tap_bn[t],
+                        a.tap_bk[t] + kc * 64);
+        } else {
+          tma_load_2d(sB, &tmB, bar, a.tap_bk[t] + kc * 64, nt * BN);
+        }
+      };
+      if (resident && blockIdx.x < total_tiles) {
+        // the host picked a grid that is a multiple of n_tiles: this CTA's nt never changes
+        const int nt = blockIdx.x % a.n_tiles;
+        mbar_expect_tx(bfull, static_cast<uint32_t>(k_iters) * Cfg::kBBytes);
+        for (int it = 0; it < k_iters; ++it) {
+          const int t = it / a.k_chunks, kc = it - t * a.k_chunks;
+          load_b(smem + it * Cfg::kBBytes, bfull, nt, t, kc);
+        }
+      }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int nt = tile % a.n_tiles;
         int mt = tile / a.n_tiles;
@@ -129,20 +161,12 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int it = 0; it < k_iters; ++it) {
           const int t = it / a.k_chunks, kc = it - t * a.k_chunks;
           mbar_wait(&empty[stage], phase ^ 1);
-          uint8_t* sA = smem + stage * Cfg::kStage;
-          uint8_t* sB = sA + kABytes;
+          uint8_t* sA = ring + stage * stage_stride;
           mbar_expect_tx(&full[stage], stage_tx);
           tma_load_4d(sA, &tmA, &full[stage], kc * 64 + a.tap_dc[t], cw + a.tap_dw[t],
                       ch + a.tap_dh[t], cn);
-          if (B_MN) {
-#pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              tma_load_2d(sB + j * 8192, &tmB, &full[stage], nt * BN + j * 64 + a.tap_bn[t],
-                          a.tap_bk[t] + kc * 64);
-          } else {
-            tma_load_2d(sB, &tmB, &full[stage], a.tap_bk[t] + kc * 64, nt * BN);
-          }
-          if (++stage == Cfg::kStages) {
+          if (!resident) load_b(sA + kABytes, &full[stage], nt, t, kc);
+          if (++stage == nstages) {
             stage = 0;
             phase ^= 1;
           }
@@ -157,6 +181,7 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      if (resident && blockIdx.x < total_tiles) mbar_wait(bfull, 0);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -164,8 +189,9 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int it = 0; it < k_iters; ++it) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(smem + stage * Cfg::kStage);
-          const uint32_t b_base = a_base + kABytes;
+          const uint32_t a_base = smem_u32(ring + stage * stage_stride);
+          const uint32_t b_base =
+              resident ? smem_u32(smem + it * Cfg::kBBytes) : a_base + kABytes;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint64_t adesc = umma_desc_sw128(a_base + k * 32, 16, 1024);
@@ -174,7 +200,7 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             umma_bf16(d_tmem, adesc, bdesc, idesc, (it | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty[stage]);
-          if (++stage == Cfg::kStages) {
+          if (++stage == nstages) {
             stage = 0;
             phase ^= 1;
           }
@@ -198,6 +224,18 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t stg = smem_u32(out_stage + ew * 4096);
     int acc = 0;
     uint32_t acc_phase = 0;
+    // position of this thread's accumulator row inside the pixel box: tile independent
+    const int row = q * 32 + lane;
+    const int iw = row % a.box_w;
+    const int ih = (row / a.box_w) % a.box_h;
+    const int in_ = row / (a.box_w * a.box_h);
+    // fused statistics: lane l keeps the running sums of columns (2l, 2l+1) of its slabs in
+    // registers for as long as the CTA stays on one n tile; they meet in shared memory only
+    // when the n tile changes or the CTA runs out of tiles (see the flush below)
+    constexpr int kSlabs = BN >= 128 ? BN / 128 : 1;
+    float2 rs[kSlabs], rq[kSlabs];
+#pragma unroll
+    for (int i = 0; i < kSlabs; ++i) rs[i] = rq[i] = make_float2(0.f, 0.f);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int nt = tile % a.n_tiles;
       int mt = tile / a.n_tiles;
@@ -205,10 +243,6 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mt /= a.tiles_w;
       const int th = mt % a.tiles_h;
       const int tn = mt / a.tiles_h;
-      const int row = q * 32 + lane;
-      const int iw = row % a.box_w;
-      const int ih = (row / a.box_w) % a.box_h;
-      const int in_ = row / (a.box_w * a.box_h);
       const int w = tw * a.box_w + iw, h = th * a.box_h + ih, n = tn * a.box_n + in_;
       const bool valid = row < rows && w < a.lim_w && h < a.lim_h && n < a.lim_n;
       const long long pix =
@@ -229,8 +263,10 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         long long roffs[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) roffs[i] = __shfl_sync(0xffffffff, off, i * 4 + (lane >> 3));
-#pragma unroll 1
-        for (int c = half; c < BN / 64; c += 2) {
+#pragma unroll
+        for (int ci = 0; ci < kSlabs; ++ci) {
+          const int c = half + 2 * ci;
+          if (c >= BN / 64) break;
           // accumulate mode: the previous values do not depend on the MMA - issue all eight
           // 16-byte loads of this slab now so their latency overlaps the TMEM read + staging
           uint4 prev[8];
@@ -298,11 +334,8 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               sacc = __fadd2_rn(sacc, xy);        // packed fp32x2 pipe (sm_100)
               qacc = __ffma2_rn(xy, xy, qacc);
             }
-            float* st = stat_smem + (c * 64 + 2 * lane) * 2;
-            red_shared_add(st + 0, sacc.x);
-            red_shared_add(st + 1, qacc.x);
-            red_shared_add(st + 2, sacc.y);
-            red_shared_add(st + 3, qacc.y);
+            rs[ci] = __fadd2_rn(rs[ci], sacc);
+            rq[ci] = __fadd2_rn(rq[ci], qacc);
           }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -428,7 +461,21 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
-      if (do_stats) {
+      const int next_tile = tile + gridDim.x;
+      if (do_stats && (next_tile >= total_tiles || next_tile % a.n_tiles != nt)) {
+        // flush: registers -> shared (four row quarters meet per column) -> global atomics
+#pragma unroll
+        for (int ci = 0; ci < kSlabs; ++ci) {
+          const int c = half + 2 * ci;
+          if (c < BN / 64) {
+            float* st = stat_smem + (c * 64 + 2 * lane) * 2;
+            red_shared_add(st + 0, rs[ci].x);
+            red_shared_add(st + 1, rq[ci].x);
+            red_shared_add(st + 2, rs[ci].y);
+            red_shared_add(st + 3, rq[ci].y);
+          }
+          rs[ci] = rq[ci] = make_float2(0.f, 0.f);
+        }
         asm volatile("bar.sync 1, 256;" ::: "memory");
         for (int c = et; c < BN; c += kEpiThreads) {
           const int col = nt * BN + c;
@@ -564,6 +611,33 @@ IGemmPlan* igemm_plan_fwd(const TmapDesc& a, const TmapDesc& b, const FwdArgs& a
   p->b_mn = b_mn;
   p->total_work = args.n_tiles * args.tiles_w * args.tiles_h * args.tiles_n;
   p->grid = p->total_work < num_sms ? p->total_work : num_sms;
+  // a grid that is a multiple of n_tiles pins every CTA to one n tile: the fused statistics
+  // then stay in registers until the CTA is done, and the filter tile can stay resident
+  if (args.n_tiles > 1 && args.n_tiles <= 8 && p->total_work >= 2 * num_sms)
+    p->grid = num_sms - num_sms % args.n_tiles;
+  // weight-stationary mode (see kMinAStages): every CTA must keep one n tile for its whole
+  // tile list (grid multiple of n_tiles) and run several tiles so that the B load amortises
+  p->fa.b_resident = 0;
+  p->fa.a_stages = 0;
+  static const bool allow_resident = [] {
+    const char* e = getenv("TFOS_B_RESIDENT");
+    return e == nullptr || atoi(e) != 0;
+  }();
+  const int k_iters = args.num_taps * args.k_chunks;
+  const long long ring_bytes = bn == 64    ? FwdCfg<64>::kStages * FwdCfg<64>::kStage
+                               : bn == 128 ? FwdCfg<128>::kStages * FwdCfg<128>::kStage
+                                           : FwdCfg<256>::kStages * FwdCfg<256>::kStage;
+  const long long b_bytes = static_cast<long long>(k_iters) * bn * 128;
+  if (allow_resident && args.n_tiles <= 8 && p->total_work >= 2 * num_sms &&
+      b_bytes + kMinAStages * kABytes <= ring_bytes) {
+    const int grid = num_sms - num_sms % args.n_tiles;
+    if (grid > 0) {
+      long long st = (ring_bytes - b_bytes) / kABytes;
+      p->fa.a_stages = static_cast<int>(st > kMaxStages ? kMaxStages : st);
+      p->fa.b_resident = 1;
+      p->grid = grid;
+    }
+  }
   return p;
 }
 

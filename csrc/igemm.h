@@ -46,6 +46,7 @@ struct FwdArgs {
   float* col_sum;           // optional fused per-column sum / sum of squares
   float* col_sumsq;         //   (batch-norm statistics of the stored tensor)
   void* out;
+  int b_resident, a_stages;  // set by igemm_plan_fwd: weight-stationary mode (igemm.cu)
 };
 
 // weight-gradient problems: K = pixels, M = Cout, N = Cin (per tap).

@@ -126,7 +126,10 @@ def _conv_case(N, H, W, Ci, Co, k, stride):
 
 CONV_CASES = [(2, 16, 16, 64, 64, 3, 1), (4, 56, 56, 64, 128, 3, 1), (2, 14, 14, 256, 256, 3, 1),
               (3, 7, 7, 128, 512, 3, 1), (2, 28, 28, 128, 128, 3, 2), (2, 56, 56, 256, 512, 1, 2),
-              (2, 15, 15, 64, 64, 3, 2), (2, 8, 8, 16, 24, 3, 1)]
+              (2, 15, 15, 64, 64, 3, 2), (2, 8, 8, 16, 24, 3, 1),
+              # >= 2 tiles per SM with a small filter: the weight-stationary (B resident) mode
+              (16, 56, 56, 64, 64, 3, 1), (16, 56, 56, 64, 256, 1, 1), (32, 28, 28, 128, 512, 1, 1),
+              (64, 14, 14, 256, 1024, 1, 1)]
 
 
 @check
