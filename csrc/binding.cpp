@@ -202,13 +202,18 @@ void bn_inference_coeffs(const Tensor& gamma, const Tensor& beta, const Tensor& 
         "bn_inference_coeffs");
 }
 void bn_apply(const Tensor& x, c10::optional<Tensor> residual, const Tensor& scale,
-              const Tensor& shift, Tensor y, int act) {
+              const Tensor& shift, Tensor y, int act, c10::optional<Tensor> mask) {
   need(x, torch::kBFloat16, "x");
   need(y, torch::kBFloat16, "y");
   const int C = x.size(-1);
   TORCH_CHECK(C % 8 == 0, "bn_apply: C % 8");
+  if (mask.has_value())
+    TORCH_CHECK(mask->scalar_type() == torch::kUInt8 && mask->numel() * 8 == x.numel(),
+                "bn_apply: mask must be uint8 with numel/8 entries");
   check(tfos::bn_apply(x.data_ptr(), optptr(residual), scale.data_ptr<float>(),
-                       shift.data_ptr<float>(), y.data_ptr(), x.numel() / C, C, act, cur_stream()),
+                       shift.data_ptr<float>(), y.data_ptr(),
+                       mask.has_value() ? mask->data_ptr<uint8_t>() : nullptr, x.numel() / C, C,
+                       act, cur_stream()),
         "bn_apply");
 }
 void bn_bwd_reduce(const Tensor& dy, const Tensor& x, c10::optional<Tensor> y, const Tensor& mean,
@@ -492,7 +497,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("bn_stats", &bn_stats);
   m.def("bn_finalize", &bn_finalize);
   m.def("bn_inference_coeffs", &bn_inference_coeffs);
-  m.def("bn_apply", &bn_apply);
+  m.def("bn_apply", &bn_apply, py::arg("x"), py::arg("residual"), py::arg("scale"),
+        py::arg("shift"), py::arg("y"), py::arg("act"), py::arg("mask") = py::none());
   m.def("bn_bwd_reduce", &bn_bwd_reduce);
   m.def("bn_bwd_apply", &bn_bwd_apply);
   m.def("add_act", &add_act);

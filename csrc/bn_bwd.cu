@@ -6,6 +6,8 @@
 //   relu 0  no ReLU (projection shortcut branch)
 //   relu 1  mask from the stored output y (unit with a residual input)
 //   relu 2  mask recomputed from x with the forward scale/shift (no residual) - y is not read.
+//   relu 3  mask read from the bit mask the forward bn_apply stored (y points at it: one byte
+//           per 8 channels instead of 16 - a residual unit's backward reads 1/16 of y's bytes)
 // Both kernels are latency bound unless enough bytes are in flight, so every thread owns one
 // 8-channel group (per-channel coefficients live in registers) and issues the 16-byte loads of
 // FOUR rows before touching any of them.
@@ -78,6 +80,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
       for (long long p = static_cast<long long>(blockIdx.x) * G.rl + G.r_in; p < P;
            p += kRows * stride) {
         uint4 gq[kRows], xq[kRows], yq[kRows];
+        uint32_t mq[kRows];
 #pragma unroll
         for (int k = 0; k < kRows; ++k) {
           const long long pk = p + k * stride;
@@ -86,6 +89,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
           gq[k] = in ? ld_nc_v4(dy + o) : zero;
           xq[k] = in ? ld_nc_v4(x + o) : zero;
           yq[k] = (in && relu == 1) ? ld_nc_v4(y + o) : zero;
+          mq[k] = (in && relu == 3) ? __ldg(reinterpret_cast<const uint8_t*>(y) + (o >> 3)) : 0u;
         }
 #pragma unroll
         for (int k = 0; k < kRows; ++k) {
@@ -95,7 +99,10 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
           if (relu == 1) unpack8(yq[k], yv);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float pre = relu == 2 ? xv[j] * fs[j] + fh[j] : (relu == 1 ? yv[j] : 1.f);
+            const float pre = relu == 2   ? xv[j] * fs[j] + fh[j]
+                              : relu == 1 ? yv[j]
+                              : relu == 3 ? (((mq[k] >> j) & 1u) ? 1.f : 0.f)
+                                          : 1.f;
             const float gj = pre > 0.f ? gv[j] : 0.f;
             a0[j] += gj * (xv[j] - mu[j]);
             a1[j] += gj;
@@ -154,6 +161,7 @@ bn_bwd_apply_kernel(const __nv_bfloat16* dy, const __nv_bfloat16* __restrict__ x
     for (long long p = static_cast<long long>(blockIdx.x) * G.rl + G.r_in; p < P;
          p += kRows * stride) {
       uint4 gq[kRows], xq[kRows], yq[kRows];
+      uint32_t mq[kRows];
 #pragma unroll
       for (int k = 0; k < kRows; ++k) {
         const long long pk = p + k * stride;
@@ -162,6 +170,7 @@ bn_bwd_apply_kernel(const __nv_bfloat16* dy, const __nv_bfloat16* __restrict__ x
         gq[k] = in ? *reinterpret_cast<const uint4*>(dy + o) : zero;  // may alias dres: no .nc
         xq[k] = in ? ld_nc_v4(x + o) : zero;
         yq[k] = (in && relu == 1) ? ld_nc_v4(y + o) : zero;
+        mq[k] = (in && relu == 3) ? __ldg(reinterpret_cast<const uint8_t*>(y) + (o >> 3)) : 0u;
       }
 #pragma unroll
       for (int k = 0; k < kRows; ++k) {
@@ -174,7 +183,10 @@ bn_bwd_apply_kernel(const __nv_bfloat16* dy, const __nv_bfloat16* __restrict__ x
         if (relu == 1) unpack8(yq[k], yv);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float pre = relu == 2 ? xv[j] * fs[j] + fh[j] : (relu == 1 ? yv[j] : 1.f);
+          const float pre = relu == 2   ? xv[j] * fs[j] + fh[j]
+                            : relu == 1 ? yv[j]
+                            : relu == 3 ? (((mq[k] >> j) & 1u) ? 1.f : 0.f)
+                                        : 1.f;
           gv[j] = pre > 0.f ? gv[j] : 0.f;
           ov[j] = cA[j] * gv[j] + cB[j] * xv[j] + cK[j];
         }

@@ -17,8 +17,9 @@ cudaError_t bn_finalize(float* sum, float* sumsq, const float* gamma, const floa
 cudaError_t bn_inference_coeffs(const float* gamma, const float* beta, const float* rm,
                                 const float* rv, float* scale, float* shift, int C, float eps,
                                 cudaStream_t s);
+// mask (optional): one bit per element, set where the pre-activation value is > 0
 cudaError_t bn_apply(const void* x, const void* residual, const float* scale, const float* shift,
-                     void* y, long long P, int C, int act, cudaStream_t s);
+                     void* y, uint8_t* mask, long long P, int C, int act, cudaStream_t s);
 cudaError_t bn_bwd_reduce(const void* dy, const void* x, const void* y, const float* mean,
                           const float* invstd, const float* fscale, const float* fshift,
                           long long P, int C, int relu, float* dgamma, float* dbeta,

@@ -134,6 +134,17 @@ class BatchNorm(object):
 
   def forward(self, x_raw, y, residual=None, act=1, training=True, fused_stats=True):
     count = x_raw.numel() // self.C
+    # a residual unit's ReLU mask depends on the sum, not on x alone: keep it as one bit per
+    # element so that the backward pass does not have to re-read the whole bf16 output
+    # (the buffer is never released: a captured CUDA graph may hold its address)
+    if training and residual is not None and act == 1:
+      buf = getattr(self, "_mask_buf", None)
+      if buf is None or buf.numel() * 8 != x_raw.numel():
+        buf = self._mask_buf = torch.empty(x_raw.numel() // 8, dtype=torch.uint8,
+                                           device=x_raw.device)
+      self.mask = buf
+    else:
+      self.mask = None
     if training:
       if not fused_stats:
         ops.K.bn_stats(x_raw, self.sum, self.sumsq)
@@ -143,16 +154,19 @@ class BatchNorm(object):
     else:
       ops.K.bn_inference_coeffs(self.gamma, self.beta, self.running_mean, self.running_var,
                                 self.scale, self.shift, self.eps)
-    ops.K.bn_apply(x_raw, residual, self.scale, self.shift, y, act)
+    ops.K.bn_apply(x_raw, residual, self.scale, self.shift, y, act, self.mask)
 
   def backward(self, dy, x_raw, y, dx, dres=None, relu=True, residual=False):
     """relu mask: recomputed from x_raw with the forward scale/shift when the unit has no
     residual input (saves reading y: 2 of 6-8 bytes per element); from the stored y otherwise."""
     mode = 0 if not relu else (1 if (residual or dres is not None) else 2)
-    ops.K.bn_bwd_reduce(dy, x_raw, y if mode == 1 else None, self.mean, self.invstd, self.dgamma,
-                        self.dbeta, mode, self.scale, self.shift)
-    ops.K.bn_bwd_apply(dy, x_raw, y if mode == 1 else None, self.gamma, self.mean, self.invstd,
-                       self.dgamma, self.dbeta, dx, dres, mode, self.scale, self.shift)
+    ysrc = y if mode == 1 else None
+    if mode == 1 and getattr(self, "mask", None) is not None:
+      mode, ysrc = 3, self.mask   # bit mask written by forward(): 1/16 of y's bytes
+    ops.K.bn_bwd_reduce(dy, x_raw, ysrc, self.mean, self.invstd, self.dgamma, self.dbeta, mode,
+                        self.scale, self.shift)
+    ops.K.bn_bwd_apply(dy, x_raw, ysrc, self.gamma, self.mean, self.invstd, self.dgamma,
+                       self.dbeta, dx, dres, mode, self.scale, self.shift)
 
 
 class Conv(object):

@@ -36,6 +36,7 @@ def main():
     y = torch.relu(x)
     res = torch.randn(P, C, device="cuda").bfloat16()
     out = torch.empty_like(x)
+    bits = torch.zeros(P * C // 8, dtype=torch.uint8, device="cuda")
     z = lambda: torch.zeros(C, device="cuda")  # noqa: E731
     mean, invstd, gamma, dg, db, sc, sh = z(), z() + 1, z() + 1, z(), z(), z() + 1, z()
     n = P * C * 2 / 1e3  # KB per tensor pass
@@ -45,6 +46,8 @@ def main():
         ("bwd_reduce m1", lambda: K.bn_bwd_reduce(dy, x, y, mean, invstd, dg, db, 1, None, None), 3),
         ("bwd_apply m2", lambda: K.bn_bwd_apply(dy, x, None, gamma, mean, invstd, dg, db, out, None, 2, sc, sh), 3),
         ("bwd_apply m1+dres", lambda: K.bn_bwd_apply(dy, x, y, gamma, mean, invstd, dg, db, out, res, 1, None, None), 5),
+        ("bwd_reduce m3", lambda: K.bn_bwd_reduce(dy, x, bits, mean, invstd, dg, db, 3, None, None), 2.0625),
+        ("bwd_apply m3+dres", lambda: K.bn_bwd_apply(dy, x, bits, gamma, mean, invstd, dg, db, out, res, 3, None, None), 4.0625),
     ]
     for name, fn, passes in cases:
       us = timeit(fn)

@@ -261,6 +261,20 @@ def batchnorm():
     ok &= _report("bn dx", _rel(dx, xf.grad), 3e-2)
     mask = (yr > 0).float()
     ok &= _report("bn dres", _rel(dres, dy.float() * mask), 2e-2)
+    # bit mask written by the forward kernel (mode 3) == mask taken from the stored y (mode 1)
+    if C % 8 == 0:
+      bits = torch.zeros(P * C // 8, dtype=torch.uint8, device="cuda")
+      y3 = torch.empty_like(x)
+      K.bn_apply(x, res, scale, shift, y3, 1, bits)
+      d3, b3 = z(), z()
+      dx3, dres3 = torch.empty_like(x), torch.empty_like(x)
+      K.bn_bwd_reduce(dy, x, bits, mean, invstd, d3, b3, 3, None, None)
+      K.bn_bwd_apply(dy, x, bits, gamma, mean, invstd, d3, b3, dx3, dres3, 3, None, None)
+      torch.cuda.synchronize()
+      ok &= _report("bn bitmask fwd", _rel(y3, y), 1e-9)
+      ok &= _report("bn bitmask dgamma", _rel(d3, dgamma), 1e-5)
+      ok &= _report("bn bitmask dx", _rel(dx3, dx), 2e-3)  # dgamma: atomic order
+      ok &= _report("bn bitmask dres", _rel(dres3, dres), 1e-9)
     # no-residual unit: ReLU mask recomputed from x (mode 2) must match the stored-y mask (mode 1)
     y2 = torch.empty_like(x)
     K.bn_apply(x, None, scale, shift, y2, 1)
