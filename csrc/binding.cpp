@@ -117,6 +117,7 @@ int64_t plan_fwd(const py::dict& a, const py::dict& b, const py::dict& g, int bn
   f.relu = geti<int>(g, "relu", 0);
   f.out_fp32 = geti<int>(g, "out_fp32", 0);
   f.accumulate = geti<int>(g, "accumulate", 0);
+  f.stem = geti<int>(g, "stem", 0);
   f.bias = reinterpret_cast<const float*>(geti<uint64_t>(g, "bias", 0));
   f.col_sum = reinterpret_cast<float*>(geti<uint64_t>(g, "col_sum", 0));
   f.col_sumsq = reinterpret_cast<float*>(geti<uint64_t>(g, "col_sumsq", 0));
@@ -152,6 +153,7 @@ int64_t plan_wgrad(const py::dict& a, const py::dict& b, const py::dict& g, int 
   w.m_valid = geti<int>(g, "m_valid", 0);
   w.n_valid = geti<int>(g, "n_valid", 0);
   w.ldw = geti<int>(g, "ldw", 0);
+  w.stem = geti<int>(g, "stem", 0);
   w.dw = reinterpret_cast<float*>(geti<uint64_t>(g, "dw", 0));
   TORCH_CHECK(w.dw != nullptr && w.ldw > 0, "igemm wgrad: dw/ldw");
   char err[512] = {0};

@@ -60,6 +60,14 @@ struct FwdCfg {
 // those layers are bound by the ~6 KB/clk L2->SM fabric, not by HBM or the tensor pipe.
 constexpr int kMaxStages = 12;
 constexpr int kMinAStages = 4;
+// Stem mode (ResNet 7x7/2 on the window-row layout, ops/igemm.py): a tile is 8 x 16 output
+// pixels; its A stage is ONE TMA box of 8 window columns x 37 input rows (2*16 + 5) from which
+// all seven filter rows are read through the UMMA descriptor - filter row r of output row j is
+// box row 2j + r, so the 8-row core-matrix groups sit 2 box rows (2048 B) apart (SBO) and the
+// filter row only shifts the start address by 1024 B.  L2 -> SM traffic per tile: 37 KB instead
+// of 7 x 16 KB of A plus 7 x 8 KB of B (the filter is resident).
+constexpr int kStemBoxW = 8, kStemBoxH = 16, kStemRows = 2 * kStemBoxH + 5;
+constexpr int kStemStage = kStemBoxW * kStemRows * 128;  // 37888 B, a multiple of 1024
 
 __device__ __forceinline__ void red_shared_add(float* p, float v) {
   asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(smem_u32(p)), "f"(v) : "memory");
@@ -121,10 +129,13 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int k_iters = a.num_taps * a.k_chunks;
   const int rows = a.box_w * a.box_h * a.box_n;
   const bool resident = a.b_resident != 0;
+  const bool stem = a.stem != 0;  // implies resident
   const int nstages = resident ? a.a_stages : Cfg::kStages;
-  const uint32_t stage_stride = resident ? kABytes : Cfg::kStage;
+  const uint32_t stage_stride = stem ? kStemStage : (resident ? kABytes : Cfg::kStage);
   uint8_t* const ring = smem + (resident ? k_iters * Cfg::kBBytes : 0);  // B region first
-  const uint32_t stage_tx = static_cast<uint32_t>(rows) * 128u + (resident ? 0u : Cfg::kBBytes);
+  const uint32_t stage_tx =
+      stem ? kStemStage
+           : static_cast<uint32_t>(rows) * 128u + (resident ? 0u : Cfg::kBBytes);
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -158,6 +169,17 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int th = mt % a.tiles_h;
         const int tn = mt / a.tiles_h;
         const int cw = tw * a.box_w * a.mul_w, ch = th * a.box_h * a.mul_h, cn = tn * a.box_n;
+        if (stem) {  // one halo box per tile
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], stage_tx);
+          tma_load_4d(ring + stage * stage_stride, &tmA, &full[stage], 0, cw + a.tap_dw[0],
+                      ch + a.tap_dh[0], cn);
+          if (++stage == nstages) {
+            stage = 0;
+            phase ^= 1;
+          }
+          continue;
+        }
         for (int it = 0; it < k_iters; ++it) {
           const int t = it / a.k_chunks, kc = it - t * a.k_chunks;
           mbar_wait(&empty[stage], phase ^ 1);
@@ -186,7 +208,27 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int it = 0; it < k_iters; ++it) {
+        if (stem) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(ring + stage * stage_stride);
+          for (int r = 0; r < 7; ++r) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t adesc =
+                  umma_desc_sw128(a_base + r * (kStemBoxW * 128) + k * 32, 16, 2 * kStemBoxW * 128);
+              const uint64_t bdesc =
+                  umma_desc_sw128(smem_u32(smem + r * Cfg::kBBytes) + k * 32, 16, 1024);
+              umma_bf16(d_tmem, adesc, bdesc, idesc, (r | k) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == nstages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        for (int it = 0; it < (stem ? 0 : k_iters); ++it) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t a_base = smem_u32(ring + stage * stage_stride);
@@ -628,7 +670,16 @@ IGemmPlan* igemm_plan_fwd(const TmapDesc& a, const TmapDesc& b, const FwdArgs& a
                                : bn == 128 ? FwdCfg<128>::kStages * FwdCfg<128>::kStage
                                            : FwdCfg<256>::kStages * FwdCfg<256>::kStage;
   const long long b_bytes = static_cast<long long>(k_iters) * bn * 128;
-  if (allow_resident && args.n_tiles <= 8 && p->total_work >= 2 * num_sms &&
+  if (args.stem) {
+    if (bn != 64 || b_mn || args.num_taps != 7 || args.k_chunks != 1 || args.n_tiles != 1 ||
+        args.box_w != kStemBoxW || args.box_h != kStemBoxH || args.box_n != 1) {
+      snprintf(err, errlen, "stem mode: needs bn 64, 7 taps, one K chunk, an 8x16x1 pixel box");
+      delete p;
+      return nullptr;
+    }
+    p->fa.b_resident = 1;
+    p->fa.a_stages = static_cast<int>((ring_bytes - b_bytes) / kStemStage);
+  } else if (allow_resident && args.n_tiles <= 8 && p->total_work >= 2 * num_sms &&
       b_bytes + kMinAStages * kABytes <= ring_bytes) {
     const int grid = num_sms - num_sms % args.n_tiles;
     if (grid > 0) {
@@ -663,6 +714,15 @@ IGemmPlan* igemm_plan_wgrad(const TmapDesc& a, const TmapDesc& b, const WgradArg
   p->kind = 1;
   p->bn = bn;
   p->total_work = args.num_taps * args.m_tiles * args.n_tiles * args.k_splits;
+  if (args.stem) {  // igemm_wgrad_stem_kernel: all seven filter rows in one work item
+    if (bn != 64 || args.box_w != 16 || args.box_h != 8 || args.box_n != 1 || args.m_valid > 64 ||
+        args.m_tiles != 1 || args.n_tiles != 1) {
+      snprintf(err, errlen, "stem wgrad: needs bn 64, a 16x8x1 pixel box and Cout <= 64");
+      delete p;
+      return nullptr;
+    }
+    p->total_work = args.k_splits;
+  }
   p->grid = p->total_work < num_sms ? p->total_work : num_sms;
   return p;
 }

@@ -47,6 +47,9 @@ struct FwdArgs {
   float* col_sumsq;         //   (batch-norm statistics of the stored tensor)
   void* out;
   int b_resident, a_stages;  // set by igemm_plan_fwd: weight-stationary mode (igemm.cu)
+  // stem mode (7x7/2 convolution on the window-row layout, see igemm.cu): ONE halo box of
+  // 2*box_h+5 input rows per tile serves all seven filter rows; box_w must be 8
+  int stem;
 };
 
 // weight-gradient problems: K = pixels, M = Cout, N = Cin (per tap).
@@ -62,6 +65,7 @@ struct WgradArgs {
   int m_valid, n_valid;           // Cout, Cin
   int ldw;                        // dW row pitch in elements (= taps * Cin)
   float* dw;                      // fp32, accumulated with red.global.add
+  int stem;                       // 7x7/2 stem: all seven filter rows from one halo box
 };
 
 struct IGemmPlan {

@@ -23,6 +23,8 @@ _launches = 0
 # weight-gradient tiling knobs (tools/bench_igemm.py sweeps them)
 _WGRAD_WIDE = os.environ.get("TFOS_WGRAD_WIDE", "0") == "1"
 _WGRAD_WORK = int(os.environ.get("TFOS_WGRAD_WORK", "0"))  # 0: per-layer heuristic
+_STEM_HALO = os.environ.get("TFOS_STEM_HALO", "1") == "1"
+_STEM_SPLITS = int(os.environ.get("TFOS_STEM_SPLITS", "148"))
 
 
 def launch_count():
@@ -333,12 +335,39 @@ def _stem_tmap(xp, N, H, Wp, OW, box, es_h):
   }
 
 
+def _stem_halo_tmap(xp, N, H, Wp, OW, bw, rows):
+  """Window-row view of xp with input rows at stride 1: one box = bw window columns x rows."""
+  return {
+      "base": xp.data_ptr(),
+      "dims": [64, OW, H, N],
+      "strides": [2 * STEM_CP * 2, Wp * STEM_CP * 2, H * Wp * STEM_CP * 2],
+      "box": [64, bw, rows, 1],
+  }
+
+
 def stem_fprop(xp, w, y, bias=None, relu=False, stats=None):
   """xp [N,H,Wp,8] (image at column offset 3), w [Cout, 7, 64] (row-major taps, 8 ch each), y [N,OH,OW,Cout]."""
   N, H, Wp, _ = xp.shape
   Cout = w.shape[0]
   _, OH, OW, _ = y.shape
   bn = _bn_for(Cout)
+  if Cout <= 64 and _STEM_HALO:
+    # halo mode (csrc/igemm.cu "stem mode"): 8 x 16 output pixels per tile, one 8 x 37 box of
+    # input rows serves all seven filter rows, the packed filter stays resident in smem
+    ta = _stem_halo_tmap(xp, N, H, Wp, OW, 8, 2 * 16 + 5)
+    tb = _tmap2(w, Cout, 7 * 64, bn)
+    g = {
+        "tiles_w": -(-OW // 8), "tiles_h": -(-OH // 16), "tiles_n": N, "n_tiles": 1,
+        "box_w": 8, "box_h": 16, "box_n": 1, "mul_w": 1, "mul_h": 2,
+        "num_taps": 7, "k_chunks": 1, "stem": 1,
+        "tap_dw": [0] * 7, "tap_dh": [-STEM_PAD] * 7, "tap_bk": [r * 64 for r in range(7)],
+        "lim_w": OW, "lim_h": OH, "lim_n": N, "OW": OW, "OH": OH,
+        "ldo": Cout, "n_valid": Cout, "relu": int(relu),
+        "bias": bias.data_ptr() if bias is not None else 0, "out": y.data_ptr(),
+    }
+    _stats_args(g, stats)
+    h = _C().igemm_plan_fwd(ta, tb, g, bn, False)
+    return Plan([h], (xp, w, y, bias, stats), "stem fprop (halo)")
   bw, bh, bnn, tw, th, tn = choose_box(OW, OH, N)
   ta = _stem_tmap(xp, N, H, Wp, OW, (bw, bh, bnn), 2)
   tb = _tmap2(w, Cout, 7 * 64, bn)
@@ -361,6 +390,20 @@ def stem_wgrad(dy, xp, dw):
   """dw [Cout, 7, 64] fp32 += dy[N,OH,OW,Cout]^T windows(xp)."""
   N, OH, OW, Cout = dy.shape
   _, H, Wp, _ = xp.shape
+  if Cout <= 64 and _STEM_HALO:
+    # all seven filter rows from one 16 x 21 halo box per 16 x 8 output pixels
+    # (csrc/igemm_wgrad.cu igemm_wgrad_stem_kernel)
+    ta = _tmap4(dy, (OW, OH, N), Cout, (16, 8, 1))
+    tb = _stem_halo_tmap(xp, N, H, Wp, OW, 16, 2 * 8 + 5)
+    tw, th = -(-OW // 16), -(-OH // 8)
+    g = {
+        "tiles_w": tw, "tiles_h": th, "tiles_n": N, "box_w": 16, "box_h": 8, "box_n": 1,
+        "num_taps": 1, "tap_dw": [0], "tap_dh": [-STEM_PAD], "stem": 1,
+        "m_tiles": 1, "n_tiles": 1, "k_splits": max(1, min(_STEM_SPLITS, tw * th * N)),
+        "m_valid": Cout, "n_valid": 64, "ldw": 7 * 64, "dw": dw.data_ptr(),
+    }
+    h = _C().igemm_plan_wgrad(ta, tb, g, 64)
+    return Plan([h], (dy, xp, dw), "stem wgrad (halo)")
   bw, bh, bnn, tw, th, tn = choose_box(OW, OH, N, multiple_of=16, allow_pad=True)
   ta = _tmap4(dy, (OW, OH, N), Cout, (bw, bh, bnn))
   tb = _stem_tmap(xp, N, H, Wp, OW, (bw, bh, bnn), 2)
