@@ -40,6 +40,28 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return v;
 }
 
+__device__ __forceinline__ float2 up2(uint32_t w) {  // packed bf16 pair -> fp32 pair
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+// gradient pair masked by the ReLU that followed the batch norm (modes: see the file header)
+__device__ __forceinline__ float2 masked_g(int relu, uint32_t gw, float2 xv, uint32_t yw,
+                                           uint32_t mbits, int j, float2 fs, float2 fh) {
+  float2 g = up2(gw);
+  if (relu == 2) {
+    const float2 pre = __ffma2_rn(xv, fs, fh);
+    g.x = pre.x > 0.f ? g.x : 0.f;
+    g.y = pre.y > 0.f ? g.y : 0.f;
+  } else if (relu == 1) {
+    const float2 yv = up2(yw);
+    g.x = yv.x > 0.f ? g.x : 0.f;
+    g.y = yv.y > 0.f ? g.y : 0.f;
+  } else if (relu == 3) {
+    g.x = ((mbits >> (2 * j)) & 1u) ? g.x : 0.f;
+    g.y = ((mbits >> (2 * j + 1)) & 1u) ? g.y : 0.f;
+  }
+  return g;
+}
+
 struct Geo {
   int groups, cg, rl, g_in, r_in;
 };
@@ -64,17 +86,19 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
   const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
   for (int g0 = blockIdx.y * G.cg; g0 < G.groups; g0 += gridDim.y * G.cg) {
     const int g = g0 + G.g_in;
-    float a0[8], a1[8];
+    float2 a0[4], a1[4];  // packed fp32x2 accumulators: channels (2j, 2j+1)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) a0[j] = 0.f, a1[j] = 0.f;
+    for (int j = 0; j < 4; ++j) a0[j] = a1[j] = make_float2(0.f, 0.f);
     if (g < G.groups && G.r_in < G.rl) {
       const int c = g * 8;
-      float mu[8], fs[8], fh[8];
+      float2 nmu[4], fs[4], fh[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        mu[j] = mean[c + j];
-        fs[j] = relu == 2 ? fscale[c + j] : 0.f;
-        fh[j] = relu == 2 ? fshift[c + j] : 0.f;
+      for (int j = 0; j < 4; ++j) {
+        nmu[j] = make_float2(-mean[c + 2 * j], -mean[c + 2 * j + 1]);
+        fs[j] = relu == 2 ? make_float2(fscale[c + 2 * j], fscale[c + 2 * j + 1])
+                          : make_float2(0.f, 0.f);
+        fh[j] = relu == 2 ? make_float2(fshift[c + 2 * j], fshift[c + 2 * j + 1])
+                          : make_float2(0.f, 0.f);
       }
       const long long stride = static_cast<long long>(gridDim.x) * G.rl;
       for (long long p = static_cast<long long>(blockIdx.x) * G.rl + G.r_in; p < P;
@@ -93,34 +117,46 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
         }
 #pragma unroll
         for (int k = 0; k < kRows; ++k) {
-          float gv[8], xv[8], yv[8];
-          unpack8(gq[k], gv);
-          unpack8(xq[k], xv);
-          if (relu == 1) unpack8(yq[k], yv);
+          const uint32_t gw[4] = {gq[k].x, gq[k].y, gq[k].z, gq[k].w};
+          const uint32_t xw[4] = {xq[k].x, xq[k].y, xq[k].z, xq[k].w};
+          const uint32_t yw[4] = {yq[k].x, yq[k].y, yq[k].z, yq[k].w};
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float pre = relu == 2   ? xv[j] * fs[j] + fh[j]
-                              : relu == 1 ? yv[j]
-                              : relu == 3 ? (((mq[k] >> j) & 1u) ? 1.f : 0.f)
-                                          : 1.f;
-            const float gj = pre > 0.f ? gv[j] : 0.f;
-            a0[j] += gj * (xv[j] - mu[j]);
-            a1[j] += gj;
+          for (int j = 0; j < 4; ++j) {
+            const float2 xv = up2(xw[j]);
+            const float2 gj = masked_g(relu, gw[j], xv, yw[j], mq[k], j, fs[j], fh[j]);
+            a0[j] = __ffma2_rn(gj, __fadd2_rn(xv, nmu[j]), a0[j]);
+            a1[j] = __fadd2_rn(a1[j], gj);
           }
         }
       }
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) red[0][threadIdx.x][j] = a0[j], red[1][threadIdx.x][j] = a1[j];
+    for (int j = 0; j < 4; ++j) {
+      red[0][threadIdx.x][2 * j] = a0[j].x, red[0][threadIdx.x][2 * j + 1] = a0[j].y;
+      red[1][threadIdx.x][2 * j] = a1[j].x, red[1][threadIdx.x][2 * j + 1] = a1[j].y;
+    }
     __syncthreads();
     if (G.r_in == 0 && g < G.groups) {
+      float s0[8], s1[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float s0 = 0.f, s1 = 0.f;
+        s0[j] = 0.f, s1[j] = 0.f;
         for (int r = 0; r < G.rl; ++r)
-          s0 += red[0][r * G.cg + G.g_in][j], s1 += red[1][r * G.cg + G.g_in][j];
-        atomicAdd(dgamma + g * 8 + j, s0 * invstd[g * 8 + j]);
-        atomicAdd(dbeta + g * 8 + j, s1);
+          s0[j] += red[0][r * G.cg + G.g_in][j], s1[j] += red[1][r * G.cg + G.g_in][j];
+        s0[j] *= invstd[g * 8 + j];
+      }
+      // the L2 atomic units, not HBM, bound this kernel for wide layers (blocks x 2C atomics):
+      // 16-byte vector reductions cut the operation count 4x
+      float* dg = dgamma + g * 8;
+      float* db = dbeta + g * 8;
+      if (((reinterpret_cast<uintptr_t>(dg) | reinterpret_cast<uintptr_t>(db)) & 15) == 0) {
+        red_add_f32x4(dg, s0[0], s0[1], s0[2], s0[3]);
+        red_add_f32x4(dg + 4, s0[4], s0[5], s0[6], s0[7]);
+        red_add_f32x4(db, s1[0], s1[1], s1[2], s1[3]);
+        red_add_f32x4(db + 4, s1[4], s1[5], s1[6], s1[7]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(dg + j, s0[j]), atomicAdd(db + j, s1[j]);
       }
     }
     __syncthreads();
@@ -145,17 +181,25 @@ bn_bwd_apply_kernel(const __nv_bfloat16* dy, const __nv_bfloat16* __restrict__ x
     const int g = g0 + G.g_in;
     if (g >= G.groups) continue;
     const int c = g * 8;
-    float cA[8], cB[8], cK[8], fs[8], fh[8];
+    float2 cA[4], cB[4], cK[4], fs[4], fh[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      fs[j] = relu == 2 ? fscale[c + j] : 0.f;
-      fh[j] = relu == 2 ? fshift[c + j] : 0.f;
-      const float is = invstd[c + j];
-      const float a = gamma[c + j] * is;
-      const float b = -a * is * dgamma[c + j] * inv_count;
-      cA[j] = a;
-      cB[j] = b;
-      cK[j] = -a * dbeta[c + j] * inv_count - b * mean[c + j];
+    for (int j = 0; j < 4; ++j) {
+      float a[2], b[2], kk[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int ch = c + 2 * j + h;
+        const float is = invstd[ch];
+        a[h] = gamma[ch] * is;
+        b[h] = -a[h] * is * dgamma[ch] * inv_count;
+        kk[h] = -a[h] * dbeta[ch] * inv_count - b[h] * mean[ch];
+      }
+      cA[j] = make_float2(a[0], a[1]);
+      cB[j] = make_float2(b[0], b[1]);
+      cK[j] = make_float2(kk[0], kk[1]);
+      fs[j] = relu == 2 ? make_float2(fscale[c + 2 * j], fscale[c + 2 * j + 1])
+                        : make_float2(0.f, 0.f);
+      fh[j] = relu == 2 ? make_float2(fshift[c + 2 * j], fshift[c + 2 * j + 1])
+                        : make_float2(0.f, 0.f);
     }
     const long long stride = static_cast<long long>(gridDim.x) * G.rl;
     for (long long p = static_cast<long long>(blockIdx.x) * G.rl + G.r_in; p < P;
@@ -177,21 +221,85 @@ bn_bwd_apply_kernel(const __nv_bfloat16* dy, const __nv_bfloat16* __restrict__ x
         const long long pk = p + k * stride;
         if (pk >= P) break;
         const long long o = pk * C + c;
-        float gv[8], xv[8], yv[8], ov[8];
-        unpack8(gq[k], gv);
-        unpack8(xq[k], xv);
-        if (relu == 1) unpack8(yq[k], yv);
+        const uint32_t gw[4] = {gq[k].x, gq[k].y, gq[k].z, gq[k].w};
+        const uint32_t xw[4] = {xq[k].x, xq[k].y, xq[k].z, xq[k].w};
+        const uint32_t yw[4] = {yq[k].x, yq[k].y, yq[k].z, yq[k].w};
+        uint32_t ow[4], rw[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float pre = relu == 2   ? xv[j] * fs[j] + fh[j]
-                            : relu == 1 ? yv[j]
-                            : relu == 3 ? (((mq[k] >> j) & 1u) ? 1.f : 0.f)
-                                        : 1.f;
-          gv[j] = pre > 0.f ? gv[j] : 0.f;
-          ov[j] = cA[j] * gv[j] + cB[j] * xv[j] + cK[j];
+        for (int j = 0; j < 4; ++j) {
+          const float2 xv = up2(xw[j]);
+          const float2 gj = masked_g(relu, gw[j], xv, yw[j], mq[k], j, fs[j], fh[j]);
+          const float2 ov = __ffma2_rn(cA[j], gj, __ffma2_rn(cB[j], xv, cK[j]));
+          ow[j] = pack_bf16x2(ov.x, ov.y);
+          rw[j] = pack_bf16x2(gj.x, gj.y);
         }
-        *reinterpret_cast<uint4*>(dx + o) = pack8(ov);
-        if (dres != nullptr) *reinterpret_cast<uint4*>(dres + o) = pack8(gv);
+        *reinterpret_cast<uint4*>(dx + o) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        if (dres != nullptr)
+          *reinterpret_cast<uint4*>(dres + o) = make_uint4(rw[0], rw[1], rw[2], rw[3]);
+      }
+    }
+  }
+}
+
+// Forward apply: y = act(x * scale[c] + shift[c] (+ residual)); act 0 none, 1 relu, 2 relu6.
+// Same thread geometry as the backward kernels (a thread keeps one 8-channel group, so scale /
+// shift are loaded once, and four rows are in flight); the arithmetic runs on the packed
+// fp32x2 pipe.  mask (optional): one bit per element, set where the pre-activation is > 0.
+__global__ void __launch_bounds__(kThreads, 3)
+bn_fwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ residual,
+                    const float* __restrict__ scale, const float* __restrict__ shift,
+                    __nv_bfloat16* __restrict__ y, uint8_t* __restrict__ mask, long long P, int C,
+                    int act) {
+  const Geo G = geo(C);
+  if (G.r_in >= G.rl) return;
+  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+  const bool has_res = residual != nullptr;
+  for (int g0 = blockIdx.y * G.cg; g0 < G.groups; g0 += gridDim.y * G.cg) {
+    const int g = g0 + G.g_in;
+    if (g >= G.groups) continue;
+    const int c = g * 8;
+    float2 sc[4], sh[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      sc[j] = make_float2(scale[c + 2 * j], scale[c + 2 * j + 1]);
+      sh[j] = make_float2(shift[c + 2 * j], shift[c + 2 * j + 1]);
+    }
+    const long long stride = static_cast<long long>(gridDim.x) * G.rl;
+    for (long long p = static_cast<long long>(blockIdx.x) * G.rl + G.r_in; p < P;
+         p += kRows * stride) {
+      uint4 xq[kRows], rq[kRows];
+#pragma unroll
+      for (int k = 0; k < kRows; ++k) {
+        const long long pk = p + k * stride;
+        const bool in = pk < P;
+        const long long o = pk * C + c;
+        xq[k] = in ? ld_nc_v4(x + o) : zero;
+        rq[k] = (in && has_res) ? ld_nc_v4(residual + o) : zero;
+      }
+#pragma unroll
+      for (int k = 0; k < kRows; ++k) {
+        const long long pk = p + k * stride;
+        if (pk >= P) break;
+        const long long o = pk * C + c;
+        const uint32_t xw[4] = {xq[k].x, xq[k].y, xq[k].z, xq[k].w};
+        const uint32_t rw[4] = {rq[k].x, rq[k].y, rq[k].z, rq[k].w};
+        uint32_t ow[4], bits = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float2 v = __ffma2_rn(make_float2(__uint_as_float(xw[j] << 16),
+                                            __uint_as_float(xw[j] & 0xffff0000u)),
+                                sc[j], sh[j]);
+          if (has_res)
+            v = __fadd2_rn(v, make_float2(__uint_as_float(rw[j] << 16),
+                                          __uint_as_float(rw[j] & 0xffff0000u)));
+          bits |= (v.x > 0.f ? 1u : 0u) << (2 * j);
+          bits |= (v.y > 0.f ? 1u : 0u) << (2 * j + 1);
+          if (act >= 1) v.x = fmaxf(v.x, 0.f), v.y = fmaxf(v.y, 0.f);
+          if (act == 2) v.x = fminf(v.x, 6.f), v.y = fminf(v.y, 6.f);
+          ow[j] = pack_bf16x2(v.x, v.y);
+        }
+        *reinterpret_cast<uint4*>(y + o) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        if (mask != nullptr) mask[o >> 3] = static_cast<uint8_t>(bits);
       }
     }
   }
@@ -216,6 +324,15 @@ inline int env_waves(const char* name, int dflt) {
 }
 
 }  // namespace
+
+cudaError_t bn_apply(const void* x, const void* residual, const float* scale, const float* shift,
+                     void* y, uint8_t* mask, long long P, int C, int act, cudaStream_t s) {
+  static const int waves = env_waves("TFOS_BN_WAVES_FWD", 3);
+  bn_fwd_apply_kernel<<<red_grid(P, C, waves), kThreads, 0, s>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(residual), scale,
+      shift, static_cast<__nv_bfloat16*>(y), mask, P, C, act);
+  return cudaGetLastError();
+}
 
 cudaError_t bn_bwd_reduce(const void* dy, const void* x, const void* y, const float* mean,
                           const float* invstd, const float* fscale, const float* fshift,

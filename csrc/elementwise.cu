@@ -127,42 +127,7 @@ __global__ void bn_inference_coeffs_kernel(const float* gamma, const float* beta
   shift[c] = beta[c] - running_mean[c] * sc;
 }
 
-// y = act(x * scale[c] + shift[c] (+ residual)); act: 0 none, 1 relu, 2 relu6
-__global__ void __launch_bounds__(256)
-bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ residual,
-                const float* __restrict__ scale, const float* __restrict__ shift,
-                __nv_bfloat16* __restrict__ y, uint8_t* __restrict__ mask, long long total8, int C,
-                int act) {
-  const int groups = C >> 3;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total8;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % groups) * 8;
-    float f[8], r[8];
-    load8(x + i * 8, f);
-    const float4 s0 = *reinterpret_cast<const float4*>(scale + c);
-    const float4 s1 = *reinterpret_cast<const float4*>(scale + c + 4);
-    const float4 h0 = *reinterpret_cast<const float4*>(shift + c);
-    const float4 h1 = *reinterpret_cast<const float4*>(shift + c + 4);
-    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-    const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-    if (residual != nullptr) load8(residual + i * 8, r);
-    uint32_t mbits = 0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float v = f[j] * sc[j] + sh[j];
-      if (residual != nullptr) v += r[j];
-      mbits |= (v > 0.f ? 1u : 0u) << j;
-      if (act >= 1) v = fmaxf(v, 0.f);
-      if (act == 2) v = fminf(v, 6.f);
-      f[j] = v;
-    }
-    store8(y + i * 8, f);
-    // one bit per element: the backward pass reads this instead of the whole bf16 output
-    if (mask != nullptr) mask[i] = static_cast<uint8_t>(mbits);
-  }
-}
-
-// (batch-norm backward lives in bn_bwd.cu)
+// (batch-norm apply and backward live in bn_bwd.cu)
 
 // generic fused elementwise: out = act(a (+ b)); and relu backward
 __global__ void __launch_bounds__(256)
@@ -640,14 +605,6 @@ cudaError_t bn_inference_coeffs(const float* gamma, const float* beta, const flo
                                 cudaStream_t s) {
   bn_inference_coeffs_kernel<<<(C + 127) / 128, 128, 0, s>>>(gamma, beta, rm, rv, scale, shift, C,
                                                              eps);
-  TFOS_RET();
-}
-cudaError_t bn_apply(const void* x, const void* residual, const float* scale, const float* shift,
-                     void* y, uint8_t* mask, long long P, int C, int act, cudaStream_t s) {
-  const long long total8 = P * (C >> 3);
-  bn_apply_kernel<<<grid_for(total8, 256, kMaxBlocks), 256, 0, s>>>(
-      static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(residual), scale,
-      shift, static_cast<__nv_bfloat16*>(y), mask, total8, C, act);
   TFOS_RET();
 }
 cudaError_t add_act(const void* a, const void* b, void* out, long long n, int act,
