@@ -148,8 +148,23 @@ def create(nslots=DEFAULT_SLOTS, slot_bytes=DEFAULT_SLOT_BYTES, name=None):
   import atexit
   name = name or new_name()
   ring = _ring_cls()(name, True, nslots, slot_bytes)
-  atexit.register(_unlink, name)  # also covers executors torn down by SIGTERM
+  atexit.register(_unlink, name)
+  _cleanups.append((_unlink, name))  # executors torn down by SIGTERM run these (run_cleanups)
   return name, ring
+
+
+_cleanups = []
+
+
+def run_cleanups():
+  """Unlink every ring this process created (called from the executors' SIGTERM handler, which
+  must not run arbitrary third-party atexit hooks half-way through an import)."""
+  while _cleanups:
+    fn, arg = _cleanups.pop()
+    try:
+      fn(arg)
+    except Exception:
+      pass
 
 
 _attached = {}

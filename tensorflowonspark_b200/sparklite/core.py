@@ -159,10 +159,11 @@ def _executor_main(index, conn, app_dir, conf, env):
     pass
   signal.signal(signal.SIGINT, signal.SIG_IGN)
   def _on_term(*_):
-    # run the atexit hooks (they unlink shared-memory feed rings), then leave without unwinding
-    import atexit
+    # unlink the shared-memory feed rings this process owns, then leave without unwinding
+    # (no generic atexit run: third-party hooks are not safe inside a signal handler)
     try:
-      atexit._run_exitfuncs()
+      from .. import shmring
+      shmring.run_cleanups()
     finally:
       os._exit(0)
 
@@ -400,6 +401,13 @@ class SparkContext(object):
     self._executors = [_ExecutorHandle(self, i) for i in range(self._num_executors)]
     with SparkContext._active_lock:
       SparkContext._active = self
+    # a driver that dies with an uncaught exception never calls stop(): without this hook the
+    # interpreter would wait forever in multiprocessing's exit handler for the (persistent,
+    # non-daemonic) executor processes.  Registered after multiprocessing's own hook -> runs first.
+    import atexit
+    import weakref
+    ref, owner = weakref.ref(self), os.getpid()
+    atexit.register(lambda: os.getpid() == owner and ref() is not None and ref().stop())
     logger.info("sparklite context %s started with %d executors (app dir %s)", self.applicationId,
                 self._num_executors, self._app_dir)
 
