@@ -2,7 +2,7 @@
 ring -> DataFeed -> pinned staging -> cudaMemcpyAsync (copy stream) -> native U-Net step
 (BASELINE.json config "segmentation U-Net InputMode.SPARK DataFeed queue").
 
-  python bench/unet_datafeed.py --gpus 1 --batch 64 --examples 1024
+  python bench/unet_datafeed.py --gpus 1 --batch 64 --examples 16384
 """
 import json
 import os
@@ -15,7 +15,7 @@ if __name__ == "__main__":
   p = argparse.ArgumentParser()
   p.add_argument("--gpus", type=int, default=1)
   p.add_argument("--batch", type=int, default=64)
-  p.add_argument("--examples", type=int, default=1024)
+  p.add_argument("--examples", type=int, default=16384)
   a = p.parse_args()
   root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
   cmd = [sys.executable, os.path.join(root, "examples", "segmentation", "segmentation_spark.py"),

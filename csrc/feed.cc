@@ -76,6 +76,21 @@ class ShmRing {
       for (uint32_t i = 0; i < nslots; ++i) slots_[i].seq.store(i);
       std::atomic_thread_fence(std::memory_order_release);
       hdr_->magic = kMagic;
+      // First-touch page faults of a fresh tmpfs mapping cost ~0.5 s per 64 MiB here - far more
+      // than the memcpy that fills a slot.  Populate the payload pages in the background
+      // (MADV_POPULATE_WRITE allocates without modifying contents, so it may race with feeders).
+      uint8_t* p = base_ + data_off;
+      const uint64_t n = slot_bytes * nslots;
+      populate_ = std::thread([p, n]() {
+#ifdef MADV_POPULATE_WRITE
+        const uint64_t step = 8ull << 20;
+        for (uint64_t o = 0; o < n; o += step)
+          if (madvise(p + o, (n - o < step) ? n - o : step, MADV_POPULATE_WRITE) != 0) break;
+#else
+        (void)p;
+        (void)n;
+#endif
+      });
     } else {
       fd = shm_open(name.c_str(), O_RDWR, 0600);
       if (fd < 0) throw std::runtime_error("shm_open(attach) failed for " + name);
@@ -94,6 +109,7 @@ class ShmRing {
     }
   }
   ~ShmRing() {
+    if (populate_.joinable()) populate_.join();
     if (pinned_) cudaHostUnregister(base_);
     if (base_ && base_ != MAP_FAILED) munmap(base_, size_);
     if (owner_) shm_unlink(name_.c_str());
@@ -183,6 +199,7 @@ class ShmRing {
   Header* hdr_ = nullptr;
   SlotMeta* slots_ = nullptr;
   bool pinned_ = false;
+  std::thread populate_;
 };
 
 }  // namespace

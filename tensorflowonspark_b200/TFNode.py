@@ -150,6 +150,8 @@ class DataFeed(object):
     self._block, self._off = None, 0   # block currently being drained
     self._ring = None
     self._prefetch = None
+    self._held_pos, self._retired, self._calls = None, [], 0   # ring slots not yet given back
+    self._views_out = False
 
   # ------------------------------------------------------------- internals
   def _attach_ring(self):
@@ -164,14 +166,16 @@ class DataFeed(object):
   def _expand(self, item):
     """Turn one queue item into a block: ('rows', list) or ('cols', [ndarray per column], tupled).
 
-    Ring blocks are copied out of the shared slot column-wise (one memcpy per column) and the
-    slot is released immediately, so feeders never wait on a slow consumer of python rows."""
+    Ring blocks stay in their shared-memory slot: the columns are zero-copy views, and the slot
+    goes back to the feeders ``HOLD_CALLS`` ``next_batch*`` calls after its last row was handed
+    out (see :meth:`_retire`) - so a batch returned by ``next_batch_arrays`` stays valid while
+    the caller stages / copies it, and nothing is copied just to free the slot."""
     if isinstance(item, marker.RingBlock):
       ring = self._attach_ring()
       from . import shmring
-      cols = [c.copy() for c in shmring.unpack_columns(ring, item)]
-      ring.release_read(item.pos)
+      cols = shmring.unpack_columns(ring, item)
       tupled = not (len(item.layout) == 1 and len(item.layout[0]) == 5)
+      self._held_pos = item.pos
       return ("cols", cols, tupled, item.nrows)
     if isinstance(item, marker.Rows):
       return ("rows", item.rows, True, len(item.rows))
@@ -184,13 +188,40 @@ class DataFeed(object):
       logger.info("next_batch() got None: end of feed")
       self.queue_in.task_done()
       self.done_feeding = True
+      self._retire_current()
       return "eof"
     if isinstance(item, marker.EndPartition):
       self.queue_in.task_done()
+      self._retire_current()
       return "end_partition"
+    self._retire_current()
     self._block, self._off = self._expand(item), 0
     self.queue_in.task_done()
     return "rows"
+
+  HOLD_CALLS = 2   # a returned batch stays valid for this many further next_batch* calls
+
+  def _retire_current(self):
+    """The block being drained is exhausted: queue its ring slot for release."""
+    pos = getattr(self, "_held_pos", None)
+    if pos is not None:
+      self._held_pos = None
+      if self._views_out:       # the caller may still be reading views of this slot
+        self._retired.append((pos, self._calls))
+      else:                     # only copies (python rows) left the slot: free it right away
+        try:
+          self._attach_ring().release_read(pos)
+        except Exception:
+          pass
+    self._views_out = False
+
+  def _release_retired(self, everything=False):
+    while self._retired and (everything or self._calls - self._retired[0][1] >= self.HOLD_CALLS):
+      pos, _ = self._retired.pop(0)
+      try:
+        self._attach_ring().release_read(pos)
+      except Exception:
+        pass
 
   def _remaining(self):
     return 0 if self._block is None else self._block[3] - self._off
@@ -212,6 +243,7 @@ class DataFeed(object):
     lo, hi = self._off, self._off + k
     self._off = hi
     if kind == "cols":
+      self._views_out = self._held_pos is not None
       return [c[lo:hi] for c in data]
     rows = data[lo:hi]
     if rows and isinstance(rows[0], (list, tuple)):
@@ -220,6 +252,8 @@ class DataFeed(object):
 
   def _fill(self, batch_size, take):
     """Common batching loop: ``take(k)`` pops k rows of the current block."""
+    self._calls += 1
+    self._release_retired()
     parts, count = [], 0
     while count < batch_size:
       if self._remaining() == 0:
@@ -278,6 +312,8 @@ class DataFeed(object):
     """Stop consuming: flag the executor as terminating and drain whatever is still queued."""
     logger.info("terminate() invoked")
     self.mgr.set("state", "terminating")
+    self._retire_current()
+    self._release_retired(everything=True)
     self._block, self._off = None, 0
     dropped = 0
     while True:

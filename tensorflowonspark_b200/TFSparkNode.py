@@ -412,8 +412,8 @@ def _safe_state(mgr):
 def _create_ring():
   from . import shmring
   try:
-    slots = int(os.environ.get("TFOS_RING_SLOTS", "8"))
-    mb = int(os.environ.get("TFOS_RING_SLOT_MB", "32"))
+    slots = int(os.environ.get("TFOS_RING_SLOTS", "4"))
+    mb = int(os.environ.get("TFOS_RING_SLOT_MB", "16"))
     name, ring = shmring.create(slots, mb << 20)
     TFSparkNode.ring, TFSparkNode.ring_name = ring, name
     TFSparkNode.mgr.set("ring", {"name": name, "nslots": slots, "slot_bytes": mb << 20})
@@ -476,8 +476,11 @@ def _await_consumption(queue, equeue, feed_timeout, what):
   while joiner.is_alive():
     if not equeue.empty():
       raise Exception("Exception in worker:\n" + equeue.get())
-    joiner.join(0.1 if waited < 2 else 1.0)
-    waited += 0.1 if waited < 2 else 1.0
+    # fine-grained at first: a partition is usually consumed within milliseconds of being posted,
+    # and the executor cannot start the next feeder task before this one returns
+    step = 0.002 if waited < 0.1 else (0.05 if waited < 2 else 1.0)
+    joiner.join(step)
+    waited += step
     if waited > feed_timeout:
       raise Exception("Timeout while feeding partition ({})".format(what))
 
