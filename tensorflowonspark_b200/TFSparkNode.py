@@ -346,6 +346,10 @@ def run(fn, tf_args, cluster_meta, tensorboard, log_dir, queues, background):
     ctx.server_addr = cluster_meta["server_addr"]
     ctx.cluster_id = cluster_meta["id"]
     _export_dist_env(ctx, ordered)
+    # one node process per GPU shares this host: bound the intra-op (OpenMP / torch) thread pools
+    my_host = util.get_ip_address()
+    local_nodes = sum(1 for n in ordered if n.get("host") == my_host) or 1
+    util.limit_intra_op_threads(local_nodes)
     if tmp_sock is not None and cluster_meta.get("release_port", True):
       tmp_sock.close()
 
@@ -468,14 +472,27 @@ def _feed(queue, ring, iterator):
   return count
 
 
-def _await_consumption(queue, equeue, feed_timeout, what):
-  """Wait until the consumer has task_done()'d everything; surface worker errors and hangs."""
+def _await_consumption(queue, equeue, feed_timeout, what, low_water=0):
+  """Wait until the consumer has task_done()'d everything; surface worker errors and hangs.
+
+  ``low_water`` > 0 (training feed): return as soon as at most that many posted chunks are
+  still waiting in the queue.  The reference joins the queue for every partition
+  (tensorflowonspark/TFSparkNode.py:505-533), which leaves the consumer idle while Spark
+  schedules the next feeder task and computes its partition; letting one chunk ride across
+  the task boundary keeps the GPU fed.  The queue is FIFO, so ordering and the end-of-feed
+  marker are unaffected; ``TFOS_FEED_LOW_WATER=0`` restores the strict behaviour."""
   joiner = threading.Thread(target=queue.join, name="feed-join", daemon=True)
   joiner.start()
   waited = 0.0
   while joiner.is_alive():
     if not equeue.empty():
       raise Exception("Exception in worker:\n" + equeue.get())
+    if low_water > 0:
+      try:
+        if queue.qsize() <= low_water:
+          return
+      except Exception:   # qsize unsupported on this platform: fall back to the strict join
+        low_water = 0
     # fine-grained at first: a partition is usually consumed within milliseconds of being posted,
     # and the executor cannot start the next feeder task before this one returns
     step = 0.002 if waited < 0.1 else (0.05 if waited < 2 else 1.0)
@@ -502,7 +519,8 @@ def train(cluster_info, cluster_meta, feed_timeout=600, qname="input"):
     else:
       logger.info("feeding partition into the %s queue", qname)
       count = _feed(queue, _ring_of(mgr), iter)
-      _await_consumption(queue, equeue, feed_timeout, "train")
+      _await_consumption(queue, equeue, feed_timeout, "train",
+                         int(os.environ.get("TFOS_FEED_LOW_WATER", "1")))
       logger.info("processed %d items in partition", count)
     if _state(mgr) == "terminating":
       # the consumer asked to stop: let the driver (streaming shutdown) know

@@ -32,6 +32,31 @@ class DevicePrefetcher(object):
     self._queue = collections.deque()
     self.bytes_per_batch = sum(int(torch.empty(s, dtype=dt).numel()) * torch.empty(0, dtype=dt)
                                .element_size() for (s, dt) in specs)
+    self._specs = specs
+    self._host = None   # pinned staging owned by the prefetcher (push_arrays)
+
+  def push_arrays(self, arrays):
+    """Stage one batch given as numpy arrays / CPU tensors (e.g. zero-copy views of a feed-ring
+    slot from ``DataFeed.next_batch_arrays``) and enqueue its async copy.
+
+    The page-locked staging buffers belong to the prefetcher and are reused round-robin; before
+    one is overwritten the host WAITS for the copy that last read it.  That wait is the
+    back-pressure of the input pipeline: the host can run at most ``depth`` batches ahead of the
+    device, however long the device is stalled (e.g. on a slower peer in the all-reduce) - an
+    unprotected staging buffer would silently feed the wrong batch."""
+    if self._host is None:
+      self._host = [[torch.empty(s, dtype=dt).pin_memory() for (s, dt) in self._specs]
+                    for _ in range(self.depth)]
+    i = self._w
+    if self._used[i]:
+      self.ready[i].synchronize()
+    import numpy as np
+    for dst, src in zip(self._host[i], arrays):
+      a = src.numpy() if isinstance(src, torch.Tensor) else np.asarray(src)
+      # plain single-threaded memcpy (or cast): torch's copy_ fans a 3 MB copy out over the
+      # whole intra-op pool, which crawls when several node processes share a CPU quota
+      np.copyto(dst.numpy(), a.reshape(dst.shape), casting="unsafe")
+    self.push(self._host[i])
 
   def push(self, host_tensors):
     """Enqueue an async copy of one batch (pinned host tensors) into the next staging slot."""

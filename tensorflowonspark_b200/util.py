@@ -60,6 +60,49 @@ def get_ip_address():
     s.close()
 
 
+def usable_cpus():
+  """CPUs this process may really use: affinity mask capped by the cgroup CPU quota."""
+  try:
+    n = len(os.sched_getaffinity(0))
+  except (AttributeError, OSError):
+    n = os.cpu_count() or 1
+  for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+    try:
+      with open(path) as f:
+        parts = f.read().split()
+      if path.endswith("cpu.max"):
+        if parts[0] != "max":
+          n = min(n, max(1, int(parts[0]) // int(parts[1])))
+      else:
+        quota = int(parts[0])
+        if quota > 0:
+          with open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as f:
+            n = min(n, max(1, quota // int(f.read())))
+      break
+    except (IOError, OSError, ValueError, IndexError):
+      continue
+  return max(1, n)
+
+
+def limit_intra_op_threads(local_nodes):
+  """Default OMP/MKL/torch thread counts for a node process that shares the host with
+  ``local_nodes - 1`` others (one process per GPU): an unbounded intra-op pool per process
+  oversubscribes the box - or its container quota - by an order of magnitude.  Explicit
+  ``OMP_NUM_THREADS`` wins."""
+  if os.environ.get("OMP_NUM_THREADS"):
+    return int(os.environ["OMP_NUM_THREADS"])
+  n = max(1, min(8, usable_cpus() // max(1, 2 * local_nodes)))
+  os.environ["OMP_NUM_THREADS"] = str(n)
+  os.environ.setdefault("MKL_NUM_THREADS", str(n))
+  try:
+    import sys
+    if "torch" in sys.modules:
+      sys.modules["torch"].set_num_threads(n)
+  except Exception:
+    pass
+  return n
+
+
 def find_in_path(path, file):
   """First ``<dir>/<file>`` that exists for the directories of a PATH-like string, else False."""
   for p in path.split(os.pathsep):
