@@ -35,10 +35,10 @@ def main_fun(args, ctx):
   max_steps = args.max_steps or int(args.num_examples * args.epochs * 0.9
                                      / ctx.world_size / args.batch_size)
   while not feed.should_stop() and step < max_steps:
-    rows = feed.next_batch(args.batch_size)
-    if len(rows) < args.batch_size:
+    cols = feed.next_batch_arrays(args.batch_size)   # [B, 785] view of the feed ring
+    if not cols or len(cols[0]) < args.batch_size:
       continue
-    arr = np.asarray(rows)
+    arr = np.asarray(cols[0])
     loss = est.step(arr[:, 1:], arr[:, 0])
     step += 1
     timer.tick(step, loss, args.batch_size * ctx.world_size)

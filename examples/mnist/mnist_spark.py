@@ -27,12 +27,12 @@ def main_fun(args, ctx):
   steps = int(args.num_examples * args.epochs * 0.9 / (args.batch_size * ctx.num_workers))
   timer = mnist_common.StepTimer()
   for step in range(steps):
-    rows = feed.next_batch(args.batch_size)
-    if len(rows) < args.batch_size:
+    # columnar fast path: one [B, 785] array sliced out of the shared-memory ring - the rows are
+    # never expanded into python lists (the reference pulls them one by one, next_batch(1))
+    cols = feed.next_batch_arrays(args.batch_size)
+    if not cols or len(cols[0]) < args.batch_size:
       break
-    labels = [r[0] for r in rows]
-    images = [r[1:] for r in rows]
-    loss = step_fn(images, labels)
+    loss = step_fn(cols[0][:, 1:], cols[0][:, 0])
     timer.tick(step, loss, args.batch_size * ctx.num_workers)
     if ctx.is_chief and args.model_dir and (step + 1) % args.save_steps == 0:
       pass  # checkpointing of the torch/native model happens at export below

@@ -184,6 +184,21 @@ def _as_columns(rows):
   if not rows:
     return None
   first = rows[0]
+  if isinstance(first, (list, tuple)) and first:
+    # a row of same-typed scalars (e.g. a CSV line: label, pixel0..pixel783) is ONE [n, len]
+    # matrix, not len(row) columns
+    kind = None
+    if all(isinstance(v, (int, np.integer)) and not isinstance(v, (bool, np.bool_)) for v in first):
+      kind = "iu"
+    elif all(isinstance(v, (float, np.floating)) for v in first):
+      kind = "f"
+    if kind is not None:
+      try:
+        arr = np.asarray(rows)
+        if arr.ndim == 2 and arr.dtype.kind in kind:
+          return [np.ascontiguousarray(arr)], False
+      except Exception:
+        pass
   if isinstance(first, (list, tuple)):
     ncol = len(first)
     cols = []
