@@ -169,8 +169,8 @@ class Server(MessageSocket):
       self.send(sock, self.reservations.get())
     elif kind == "STOP":
       logger.info("stop requested by a node")
+      self.done = True   # before the reply: the requester may look at the flag right away
       self.send(sock, "OK")
-      self.done = True
     elif kind == "PUT":
       with self._board_lock:
         self._board[msg["key"]] = msg["data"]
