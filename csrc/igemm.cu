@@ -110,7 +110,9 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], kEpiWarps);
+      // 64-column tiles are one slab wide: the two warps of a lane quarter then take ALTERNATE
+      // tiles (= alternate TMEM buffers) instead of one of them idling, see the epilogue
+      mbar_init(&tempty[i], (BN == 64 && a.n_tiles == 1) ? kEpiWarps / 2 : kEpiWarps);
     }
     mbar_init(bfull, 1);
     fence_mbar_init();
@@ -264,8 +266,7 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const bool bias_on = kGeneric && a.bias != nullptr;
     const bool relu_on = kGeneric && a.relu != 0;
     const uint32_t stg = smem_u32(out_stage + ew * 4096);
-    int acc = 0;
-    uint32_t acc_phase = 0;
+    const bool split = BN == 64 && a.n_tiles == 1;   // half-groups own alternate tiles
     // position of this thread's accumulator row inside the pixel box: tile independent
     const int row = q * 32 + lane;
     const int iw = row % a.box_w;
@@ -278,7 +279,38 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     float2 rs[kSlabs], rq[kSlabs];
 #pragma unroll
     for (int i = 0; i < kSlabs; ++i) rs[i] = rq[i] = make_float2(0.f, 0.f);
+    auto flush_stats = [&](int nt) {
+      // registers -> shared (the row quarters / half-groups meet per column) -> global atomics
+#pragma unroll
+      for (int ci = 0; ci < kSlabs; ++ci) {
+        const int c = split ? ci : half + 2 * ci;
+        if (c < BN / 64) {
+          float* st = stat_smem + (c * 64 + 2 * lane) * 2;
+          red_shared_add(st + 0, rs[ci].x);
+          red_shared_add(st + 1, rq[ci].x);
+          red_shared_add(st + 2, rs[ci].y);
+          red_shared_add(st + 3, rq[ci].y);
+        }
+        rs[ci] = rq[ci] = make_float2(0.f, 0.f);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int c = et; c < BN; c += kEpiThreads) {
+        const int col = nt * BN + c;
+        if (col < a.n_valid) {
+          atomicAdd(a.col_sum + col, stat_smem[c * 2 + 0]);
+          atomicAdd(a.col_sumsq + col, stat_smem[c * 2 + 1]);
+        }
+        stat_smem[c * 2 + 0] = 0.f;
+        stat_smem[c * 2 + 1] = 0.f;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    };
+    int it = -1;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      ++it;
+      if (split && (it & 1) != half) continue;   // the other half-group owns this tile
+      const int acc = it & 1;                    // TMEM buffer / barrier pair of this tile
+      const uint32_t acc_phase = (it >> 1) & 1;
       const int nt = tile % a.n_tiles;
       int mt = tile / a.n_tiles;
       const int tw = mt % a.tiles_w;
@@ -307,7 +339,7 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int i = 0; i < 8; ++i) roffs[i] = __shfl_sync(0xffffffff, off, i * 4 + (lane >> 3));
 #pragma unroll
         for (int ci = 0; ci < kSlabs; ++ci) {
-          const int c = half + 2 * ci;
+          const int c = split ? ci : half + 2 * ci;
           if (c >= BN / 64) break;
           // accumulate mode: the previous values do not depend on the MMA - issue all eight
           // 16-byte loads of this slab now so their latency overlaps the TMEM read + staging
@@ -414,7 +446,7 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       } else {
         // general path: fp32 output, ragged N, or unaligned pitch (dense heads, tails)
 #pragma unroll 1
-        for (int c = half; c < BN / 32; c += 2) {
+        for (int c = split ? 0 : half; c < BN / 32; c += split ? 1 : 2) {
           uint32_t v[32];
           tmem_ld_32x32(tbase + c * 32, v);
           tmem_ld_wait();
@@ -504,35 +536,11 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
       const int next_tile = tile + gridDim.x;
-      if (do_stats && (next_tile >= total_tiles || next_tile % a.n_tiles != nt)) {
-        // flush: registers -> shared (four row quarters meet per column) -> global atomics
-#pragma unroll
-        for (int ci = 0; ci < kSlabs; ++ci) {
-          const int c = half + 2 * ci;
-          if (c < BN / 64) {
-            float* st = stat_smem + (c * 64 + 2 * lane) * 2;
-            red_shared_add(st + 0, rs[ci].x);
-            red_shared_add(st + 1, rq[ci].x);
-            red_shared_add(st + 2, rs[ci].y);
-            red_shared_add(st + 3, rq[ci].y);
-          }
-          rs[ci] = rq[ci] = make_float2(0.f, 0.f);
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        for (int c = et; c < BN; c += kEpiThreads) {
-          const int col = nt * BN + c;
-          if (col < a.n_valid) {
-            atomicAdd(a.col_sum + col, stat_smem[c * 2 + 0]);
-            atomicAdd(a.col_sumsq + col, stat_smem[c * 2 + 1]);
-          }
-          stat_smem[c * 2 + 0] = 0.f;
-          stat_smem[c * 2 + 1] = 0.f;
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-      }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
+      if (!split && do_stats && (next_tile >= total_tiles || next_tile % a.n_tiles != nt))
+        flush_stats(nt);
     }
+    // split mode: the half-groups skip each other's tiles, so they meet only here (one n tile)
+    if (split && do_stats && blockIdx.x < total_tiles) flush_stats(0);
   }
 
   tc_fence_before();

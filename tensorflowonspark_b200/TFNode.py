@@ -151,7 +151,7 @@ class DataFeed(object):
     self._ring = None
     self._prefetch = None
     self._held_pos, self._retired, self._calls = None, [], 0   # ring slots not yet given back
-    self._views_out = False
+    self._views_out, self._last_take_call = False, 0
 
   # ------------------------------------------------------------- internals
   def _attach_ring(self):
@@ -207,7 +207,7 @@ class DataFeed(object):
     if pos is not None:
       self._held_pos = None
       if self._views_out:       # the caller may still be reading views of this slot
-        self._retired.append((pos, self._calls))
+        self._retired.append((pos, self._last_take_call))
       else:                     # only copies (python rows) left the slot: free it right away
         try:
           self._attach_ring().release_read(pos)
@@ -244,6 +244,7 @@ class DataFeed(object):
     self._off = hi
     if kind == "cols":
       self._views_out = self._held_pos is not None
+      self._last_take_call = self._calls   # the hold period counts from the last hand-out
       return [c[lo:hi] for c in data]
     rows = data[lo:hi]
     if rows and isinstance(rows[0], (list, tuple)):

@@ -115,3 +115,54 @@ def test_next_batch_arrays_from_ring_and_rows():
   b = feed.next_batch_arrays(8)
   assert b[0].shape[0] == 2 and int(b[1][1, 0, 0]) == 9 % 3 and feed.should_stop()
   mgr.shutdown()
+
+
+def test_array_views_stay_valid_while_feeder_reuses_slots():
+  """next_batch_arrays hands out zero-copy views of a ring slot; the slot must not go back to
+  the feeders before DataFeed.HOLD_CALLS further calls - a feeder that keeps writing must not
+  be able to scribble over a batch the consumer still holds."""
+  import numpy as np
+  mgr = TFManager.start(b"abc", ["input", "output"], "local")
+  name, ring = shmring.create(2, 1 << 16)   # 2 small slots: reuse pressure is immediate
+  mgr.set("ring", {"name": name, "nslots": 2, "slot_bytes": 1 << 16})
+  q = mgr.get_queue("input")
+
+  def block(v):
+    return shmring.pack_rows(ring, [(np.full((64,), v, np.int32),) for _ in range(8)], timeout=0.5)
+
+  q.put(block(1))
+  q.put(block(2))
+  feed = TFNode.DataFeed(mgr)
+  a = feed.next_batch_arrays(8)[0]          # all of block 1 (view into slot 0)
+  assert a.base is not None and int(a[0, 0]) == 1
+  b = feed.next_batch_arrays(8)[0]          # block 2; block 1 is exhausted but still held
+  with __import__("pytest").raises(RuntimeError):
+    block(3)                                # both slots busy: the feeder has to wait
+  assert int(a.sum()) == 8 * 64 and int(b[0, 0]) == 2
+  q.put(None)
+  assert feed.next_batch_arrays(8) == [] and feed.should_stop()   # 2 calls after block 1 ended
+  assert block(4) is not None               # ... its slot is writable again
+  mgr.shutdown()
+
+
+def test_scalar_rows_travel_as_one_matrix():
+  import numpy as np
+  mgr = TFManager.start(b"abc", ["input", "output"], "local")
+  name, ring = shmring.create(4, 1 << 20)
+  mgr.set("ring", {"name": name, "nslots": 4, "slot_bytes": 1 << 20})
+  rows = [[i] + list(range(10)) for i in range(20)]           # CSV-like: label, features
+  blk = shmring.pack_rows(ring, rows)
+  assert len(blk.layout) == 1 and blk.nrows == 20
+  q = mgr.get_queue("input")
+  q.put(blk)
+  q.put(shmring.pack_rows(ring, [[0.5, 1.5], [2.5, 3.5]]))
+  q.put(None)
+  feed = TFNode.DataFeed(mgr)
+  m = feed.next_batch_arrays(20)
+  assert len(m) == 1 and m[0].shape == (20, 11) and m[0].dtype.kind == "i"
+  assert m[0][:, 0].tolist() == list(range(20))
+  assert feed.next_batch(5) == [[0.5, 1.5], [2.5, 3.5]]       # python-row view of the same path
+  # mixed int/float rows keep their per-column types (no silent upcast of the label)
+  mixed = shmring.pack_rows(ring, [[1, 0.5], [2, 1.5]])
+  assert len(mixed.layout) == 2
+  mgr.shutdown()

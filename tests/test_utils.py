@@ -105,3 +105,15 @@ def test_injected_fault_surfaces_on_driver(sc, monkeypatch):
     cluster.shutdown()
   except Exception:
     pass
+
+
+def test_usable_cpus_and_thread_limit(monkeypatch):
+  from tensorflowonspark_b200 import util
+  n = util.usable_cpus()
+  assert 1 <= n <= (os.cpu_count() or 1)
+  monkeypatch.delenv("OMP_NUM_THREADS", raising=False)
+  monkeypatch.delenv("MKL_NUM_THREADS", raising=False)
+  t = util.limit_intra_op_threads(8)
+  assert 1 <= t <= 8 and os.environ["OMP_NUM_THREADS"] == str(t)
+  monkeypatch.setenv("OMP_NUM_THREADS", "3")
+  assert util.limit_intra_op_threads(1) == 3       # an explicit setting wins
