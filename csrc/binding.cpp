@@ -154,6 +154,7 @@ int64_t plan_wgrad(const py::dict& a, const py::dict& b, const py::dict& g, int 
   w.n_valid = geti<int>(g, "n_valid", 0);
   w.ldw = geti<int>(g, "ldw", 0);
   w.stem = geti<int>(g, "stem", 0);
+  w.wide = geti<int>(g, "wide", 0);
   w.dw = reinterpret_cast<float*>(geti<uint64_t>(g, "dw", 0));
   TORCH_CHECK(w.dw != nullptr && w.ldw > 0, "igemm wgrad: dw/ldw");
   char err[512] = {0};

@@ -722,6 +722,14 @@ IGemmPlan* igemm_plan_wgrad(const TmapDesc& a, const TmapDesc& b, const WgradArg
   p->kind = 1;
   p->bn = bn;
   p->total_work = args.num_taps * args.m_tiles * args.n_tiles * args.k_splits;
+  if (args.wide) {  // igemm_wgrad_wide_kernel: two m tiles x 256 columns per work item
+    if (bn != 256 || args.box_rows > 64) {
+      snprintf(err, errlen, "wide wgrad: needs bn 256 and pixel boxes of at most 64 rows");
+      delete p;
+      return nullptr;
+    }
+    p->total_work = args.num_taps * ((args.m_tiles + 1) / 2) * args.n_tiles * args.k_splits;
+  }
   if (args.stem) {  // igemm_wgrad_stem_kernel: all seven filter rows in one work item
     if (bn != 64 || args.box_w != 16 || args.box_h != 8 || args.box_n != 1 || args.m_valid > 64 ||
         args.m_tiles != 1 || args.n_tiles != 1) {

@@ -66,6 +66,7 @@ struct WgradArgs {
   int ldw;                        // dW row pitch in elements (= taps * Cin)
   float* dw;                      // fp32, accumulated with red.global.add
   int stem;                       // 7x7/2 stem: all seven filter rows from one halo box
+  int wide;                       // 256 x 256 tile per CTA (igemm_wgrad_wide_kernel), boxes <= 64 px
 };
 
 struct IGemmPlan {

@@ -21,7 +21,8 @@ BLOCK_M = 128
 BLOCK_K = 64
 _launches = 0
 # weight-gradient tiling knobs (tools/bench_igemm.py sweeps them)
-_WGRAD_WIDE = os.environ.get("TFOS_WGRAD_WIDE", "0") == "1"
+_WGRAD_WIDE = os.environ.get("TFOS_WGRAD_WIDE", "1") == "1"
+_WGRAD_WIDE_MIN_PIXELS = int(os.environ.get("TFOS_WGRAD_WIDE_MIN_PIXELS", "32768"))
 _WGRAD_WORK = int(os.environ.get("TFOS_WGRAD_WORK", "0"))  # 0: per-layer heuristic
 _STEM_HALO = os.environ.get("TFOS_STEM_HALO", "1") == "1"
 _STEM_SPLITS = int(os.environ.get("TFOS_STEM_SPLITS", "148"))
@@ -97,27 +98,27 @@ def _tmap2(t, rows, cols, box_rows, ld=None):
   return {"base": t.data_ptr(), "dims": [cols, rows], "strides": [ld * 2], "box": [64, box_rows]}
 
 
-def choose_box(OW, OH, N, multiple_of=1, allow_pad=False):
-  """Pick the pixel box (bw, bh, bn) with bw*bh*bn <= 128 that wastes the fewest MMA rows.
+def choose_box(OW, OH, N, multiple_of=1, allow_pad=False, max_rows=128, min_rows=1):
+  """Pick the pixel box (bw, bh, bn) with bw*bh*bn <= max_rows that wastes the fewest MMA rows.
 
   ``multiple_of`` constrains the row count (the weight-gradient kernel needs a
   multiple of 16 because pixels are its K dimension); ``allow_pad`` lets the box
   overhang the tensor (TMA zero-fills the overhang).
   """
   best = None
-  max_bw = min(128, OW + (7 if allow_pad else 0))
+  max_bw = min(max_rows, OW + (7 if allow_pad else 0))
   for bw in range(1, max_bw + 1):
     tw = -(-OW // bw)
     if not allow_pad and bw > OW:
       break
-    for bh in range(1, min(128 // bw, OH + (15 if allow_pad else 0)) + 1):
+    for bh in range(1, min(max_rows // bw, OH + (15 if allow_pad else 0)) + 1):
       th = -(-OH // bh)
       full_img = tw == 1 and th == 1
-      for bn in ([1] + ([b for b in range(2, 128 // (bw * bh) + 1)] if full_img else [])):
+      for bn in ([1] + ([b for b in range(2, max_rows // (bw * bh) + 1)] if full_img else [])):
         if bn > N:
           break
         rows = bw * bh * bn
-        if rows % multiple_of:
+        if rows % multiple_of or rows < min_rows:
           continue
         tn = -(-N // bn)
         denom = 128 if multiple_of == 1 else rows
@@ -256,25 +257,40 @@ def conv_dgrad(dy, w, dx, stride=1, pad=0, accumulate=False, relu=False, bias=No
 def _wgrad_plan(dy, dy_whn, Cout, x, x_whn, Cin, dw, ldw, taps, mul, es, box=None, c_box_b=None,
                 tap_dc=None, tap_out=None, n_valid=None):
   OW, OH, N = dy_whn
+  n_valid = Cin if n_valid is None else n_valid
+  # 256 x 256 tile per CTA (igemm_wgrad_wide_kernel): half the L2 -> SM bytes per MAC; needs
+  # 64-pixel stages, so it only pays when both channel counts fill the tile
+  # (measured, tools/bench_igemm.py: 14x14 layers -15...25 %; 7x7 layers lose to box padding)
+  wide = (_WGRAD_WIDE and Cout % 256 == 0 and n_valid % 256 == 0 and es == 1 and c_box_b is None
+          and OW * OH * N >= _WGRAD_WIDE_MIN_PIXELS)
+  if wide:
+    if box is None:
+      box = choose_box(OW, OH, N, multiple_of=16, allow_pad=True, max_rows=64, min_rows=64)
+    elif box[0] * box[1] * box[2] > 64:   # caller's 128-row GEMM box: halve it
+      assert box[1] == 1 and box[2] == 1
+      box = (64, 1, 1, -(-OW // 64), 1, 1)
   if box is None:
     box = choose_box(OW, OH, N, multiple_of=16, allow_pad=True)
   bw, bh, bnn, tw, th, tn = box
   assert (bw * bh * bnn) % 16 == 0 and bw * bh * bnn <= 128
-  n_valid = Cin if n_valid is None else n_valid
   bn = 64 if n_valid <= 64 else 128
-  if n_valid % 256 == 0 and _WGRAD_WIDE:
-    bn = 256  # fewer operand bytes per MMA: 96 instead of 128 B/clk of smem + L2 traffic
+  if wide:
+    bn = 256
   ta = _tmap4(dy, dy_whn, Cout, (bw, bh, bnn))
   if es == 1:
     tb = _tmap4(x, x_whn, Cin, (bw, bh, bnn))
   else:
     tb = _tmap4(x, x_whn, Cin, (bw * es, bh * es, bnn), es=(es, es, 1))
   m_tiles, n_tiles = -(-Cout // 128), -(-n_valid // bn)
-  out_tiles = len(taps) * m_tiles * n_tiles
+  out_tiles = len(taps) * (-(-m_tiles // 2) if wide else m_tiles) * n_tiles
   total_boxes = tw * th * tn
   # split-K work items (measured, tools/bench_igemm.py --kind wgrad): the HBM-bound 1x1 layers
   # with many pixels want one wave (fewer fp32 atomics), everything else two to four
   work = _WGRAD_WORK
+  if work == 0 and wide:
+    # 256 KB of fp32 atomics per work item and no epilogue overlap: one wave for the memory
+    # bound 1x1 layers, two for the 3x3 ones
+    work = 148 if len(taps) == 1 else 296
   if work == 0:
     if len(taps) == 1:
       work = 148 if total_boxes >= 1024 else 592
@@ -288,11 +304,11 @@ def _wgrad_plan(dy, dy_whn, Cout, x, x_whn, Cin, dw, ldw, taps, mul, es, box=Non
       "tap_dc": tap_dc if tap_dc is not None else [0] * len(taps),
       "tap_out": tap_out if tap_out is not None else [t[2] for t in taps],
       "m_tiles": m_tiles, "n_tiles": n_tiles, "k_splits": k_splits,
-      "m_valid": Cout, "n_valid": n_valid, "ldw": ldw, "dw": dw.data_ptr(),
+      "m_valid": Cout, "n_valid": n_valid, "ldw": ldw, "dw": dw.data_ptr(), "wide": int(wide),
   }
   h = _C().igemm_plan_wgrad(ta, tb, g, bn)
-  return Plan([h], (dy, x, dw), "wgrad {}->{} taps{} splits{}".format(Cin, Cout, len(taps),
-                                                                     k_splits))
+  return Plan([h], (dy, x, dw), "wgrad{} {}->{} taps{} splits{}".format(
+      " wide" if wide else "", Cin, Cout, len(taps), k_splits))
 
 
 def conv_wgrad(dy, x, dw, stride=1, pad=0):

@@ -104,7 +104,8 @@ def gemm_wgrad():
   import torch
   from tensorflowonspark_b200.ops import igemm
   ok = True
-  for (M, Co, Ci) in [(1024, 128, 64), (4096, 256, 128), (2000, 1000, 2048), (512, 64, 64)]:
+  for (M, Co, Ci) in [(1024, 128, 64), (4096, 256, 128), (2000, 1000, 2048), (512, 64, 64),
+                      (4096, 512, 256), (1000, 256, 768)]:  # the last two: wide 256x256 tiles
     dy = torch.randn(M, Co, device="cuda").bfloat16()
     x = torch.randn(M, Ci, device="cuda").bfloat16()
     dw = torch.zeros(Co, Ci, device="cuda")
@@ -189,6 +190,42 @@ def conv_wgrad():
     igemm.conv_wgrad(dy, x, dw, stride, pad).run()
     torch.cuda.synchronize()
     ok &= _report("wgrad {}".format(case), _rel(dw, wr.grad), 2e-3)
+  return ok
+
+
+@check
+def wgrad_wide():
+  """The 256 x 256-tile weight-gradient kernel, forced on for small problems too."""
+  import torch
+  from tensorflowonspark_b200.ops import igemm
+  old = igemm._WGRAD_WIDE_MIN_PIXELS
+  igemm._WGRAD_WIDE_MIN_PIXELS = 0
+  ok = True
+  try:
+    for (M, Co, Ci) in [(4096, 512, 256), (1000, 256, 768), (77, 256, 256)]:
+      dy = torch.randn(M, Co, device="cuda").bfloat16()
+      x = torch.randn(M, Ci, device="cuda").bfloat16()
+      dw = torch.zeros(Co, Ci, device="cuda")
+      p = igemm.gemm_wgrad(dy, x, dw)
+      assert "wide" in p.desc, p.desc
+      p.run()
+      torch.cuda.synchronize()
+      ok &= _report("wide gemm_wgrad {}x{}x{}".format(M, Co, Ci),
+                    _rel(dw, dy.float().t() @ x.float()), 1e-3)
+    for case in [(2, 14, 14, 256, 256, 3, 1), (3, 7, 7, 512, 256, 3, 1), (2, 14, 14, 256, 512, 1, 1)]:
+      N, H, W, Ci, Co, k, stride = case
+      x, w, OH, OW, pad = _conv_case(*case)
+      dy = torch.randn(N, OH, OW, Co, device="cuda").bfloat16()
+      wr = w.float().requires_grad_(True)
+      _conv_ref(x, wr, stride, pad).backward(dy.float())
+      dw = torch.zeros(Co, k, k, Ci, device="cuda")
+      p = igemm.conv_wgrad(dy, x, dw, stride, pad)
+      assert "wide" in p.desc, p.desc
+      p.run()
+      torch.cuda.synchronize()
+      ok &= _report("wide wgrad {}".format(case), _rel(dw, wr.grad), 2e-3)
+  finally:
+    igemm._WGRAD_WIDE_MIN_PIXELS = old
   return ok
 
 
