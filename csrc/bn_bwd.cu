@@ -25,21 +25,6 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kRows = 4;
 
-__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
-  f[0] = __uint_as_float(v.x << 16), f[1] = __uint_as_float(v.x & 0xffff0000u);
-  f[2] = __uint_as_float(v.y << 16), f[3] = __uint_as_float(v.y & 0xffff0000u);
-  f[4] = __uint_as_float(v.z << 16), f[5] = __uint_as_float(v.z & 0xffff0000u);
-  f[6] = __uint_as_float(v.w << 16), f[7] = __uint_as_float(v.w & 0xffff0000u);
-}
-__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
-  uint4 v;
-  v.x = pack_bf16x2(f[0], f[1]);
-  v.y = pack_bf16x2(f[2], f[3]);
-  v.z = pack_bf16x2(f[4], f[5]);
-  v.w = pack_bf16x2(f[6], f[7]);
-  return v;
-}
-
 __device__ __forceinline__ float2 up2(uint32_t w) {  // packed bf16 pair -> fp32 pair
   return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
 }

@@ -1,6 +1,17 @@
-import os, sys, time
-sys.path.insert(0, "/root/repo")
-import torch, torch.distributed as dist
+"""Lock-step / replica-consistency check of the fused all-reduce + optimizer under CUDA graphs:
+one rank sleeps 50 ms per step (SLOW_RANK, default 1); every rank must then take >= 50 ms per
+step, and the bf16 weights must stay bit-identical to rank 0's.
+
+  python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 \
+      tools/lockstep_check.py resnet|unet
+"""
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 local = int(os.environ.get("LOCAL_RANK", rank))
 torch.cuda.set_device(local); dev = torch.device("cuda", local)
