@@ -21,3 +21,37 @@ def test_fused_collectives_two_ranks():
                      capture_output=True, text=True, timeout=600, env=env, cwd=root)
   print(p.stdout[-4000:], p.stderr[-2000:])
   assert p.returncode == 0 and "ALL OK" in p.stdout
+
+
+@pytest.mark.parametrize("model", ["resnet", "unet"])
+def test_lockstep_and_replica_consistency_under_cuda_graphs(model):
+  """A slow rank must slow every rank down (the fused all-reduce is a real barrier inside the
+  captured graph) and the replicas' bf16 weights must stay bit-identical."""
+  import re
+  import torch
+  if torch.cuda.device_count() < 2:
+    pytest.skip("needs 2 GPUs")
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node",
+                      "2", "--master-addr", "127.0.0.1", "--master-port", "29534",
+                      os.path.join(root, "tools", "lockstep_check.py"), model],
+                     capture_output=True, text=True, timeout=600, cwd=root)
+  print(p.stdout[-3000:], p.stderr[-2000:])
+  assert p.returncode == 0
+  rows = re.findall(r"rank (\d) \w+: ([\d.]+) ms/step .*= ([\d.e+-]+)", p.stdout)
+  assert len(rows) == 2
+  for _, ms, diff in rows:
+    assert float(ms) >= 49.0 and float(diff) == 0.0
+
+
+def test_spark_bootstrap_lockstep():
+  """Same property with the communicator bootstrapped over the reservation board by Spark nodes."""
+  import torch
+  if torch.cuda.device_count() < 2:
+    pytest.skip("needs 2 GPUs")
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  p = subprocess.run([sys.executable, os.path.join(root, "tools", "lockstep_spark_check.py"),
+                      "--cluster_size", "2", "--input_mode", "spark"],
+                     capture_output=True, text=True, timeout=600, cwd=root)
+  print(p.stdout[-3000:], p.stderr[-2000:])
+  assert p.returncode == 0 and "LOCKSTEP OK" in p.stdout
