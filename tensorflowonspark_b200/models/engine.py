@@ -110,6 +110,38 @@ def normal(std):
   return lambda shape, gen: torch.randn(shape, generator=gen) * std
 
 
+# Weight gradients are needed by nobody until the optimizer runs, read only buffers that the rest
+# of the backward pass never rewrites, and are bound by the L2 -> SM fabric (profiles/): issued on
+# a side stream they overlap the HBM-bound batch-norm kernels of the layers below instead of
+# standing in the critical path.  A trainer opts in with set_wgrad_stream(); the optimizer joins
+# the stream before it consumes the gradients (FusedOptimizer.add_producer_stream).
+_wgrad_stream = None
+
+
+def set_wgrad_stream(stream):
+  global _wgrad_stream
+  _wgrad_stream = stream
+
+
+def _run_wgrad(layer):
+  """wgrad (+ bias gradient) of a Conv / Dense layer, on the side stream when one is set."""
+  def body():
+    layer.wgrad.run()
+    if layer.sbias is not None:
+      ops.K.colsum(layer.dy, layer.store.g(layer.sbias))
+  side = _wgrad_stream
+  if side is None:
+    return body()
+  main = torch.cuda.current_stream(side.device)
+  ev = getattr(layer, "_ev_dy", None)
+  if ev is None:
+    ev = layer._ev_dy = torch.cuda.Event()
+  ev.record(main)          # dy (and this step's zeroed gradient buffer) are final here
+  side.wait_event(ev)
+  with torch.cuda.stream(side):
+    body()
+
+
 class BatchNorm(object):
   """Training-mode batch norm over NHWC bf16 with statistics fused into the producer conv."""
 
@@ -219,9 +251,7 @@ class Conv(object):
     self.fwd_remote.run()
 
   def backward(self):
-    self.wgrad.run()
-    if self.sbias is not None:
-      ops.K.colsum(self.dy, self.store.g(self.sbias))
+    _run_wgrad(self)
     if self.dgrad is not None:
       self.dgrad.run()
 
@@ -259,8 +289,6 @@ class Dense(object):
     self.fwd_remote.run()
 
   def backward(self):
-    self.wgrad.run()
-    if self.sbias is not None:
-      ops.K.colsum(self.dy, self.store.g(self.sbias))
+    _run_wgrad(self)
     if self.dgrad is not None:
       self.dgrad.run()

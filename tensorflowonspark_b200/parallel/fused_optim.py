@@ -93,6 +93,21 @@ class FusedOptimizer(object):
       self.hyper[7:8].add_(1.0)
 
   # ---------------------------------------------------------------- overlap
+  def add_producer_stream(self, stream):
+    """Gradients are also written by kernels on ``stream`` (the weight-gradient side stream):
+    every consumer of the gradient buffer waits for it."""
+    if not hasattr(self, "_producers"):
+      self._producers = []
+    self._producers.append((stream, {}))
+
+  def _join_producers(self, consumer, key):
+    for stream, events in getattr(self, "_producers", []):
+      ev = events.get(key)
+      if ev is None:
+        ev = events[key] = torch.cuda.Event()
+      ev.record(stream)
+      consumer.wait_event(ev)
+
   def launch(self, tag):
     """Gradients of every bucket tagged ``tag`` are final on the current stream: run their
     fused all-reduce + update on the communication stream now."""
@@ -106,6 +121,7 @@ class FusedOptimizer(object):
         continue
       self._ev_ready[i].record(main)
       self.comm_stream.wait_event(self._ev_ready[i])
+      self._join_producers(self.comm_stream, i)
       with torch.cuda.stream(self.comm_stream):
         ops.K.allreduce_opt(self._args[i])
       self._launched.add(i)
@@ -113,6 +129,7 @@ class FusedOptimizer(object):
   def finish(self):
     """Launch whatever has not been launched and make the current stream wait for all of it."""
     if not self.overlap:
+      self._join_producers(torch.cuda.current_stream(self.device), "finish")
       return self.step()
     for tag in list(self._by_tag):
       self.launch(tag)
