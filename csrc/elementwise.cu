@@ -494,6 +494,41 @@ decode_normalize_kernel(const uint8_t* __restrict__ in, __nv_bfloat16* __restric
   }
 }
 
+// RGB -> 8 padded channels (the stem layout): four consecutive padded pixels per thread, no
+// per-channel loops or dynamic indexing - four independent 16-byte stores in flight.
+__global__ void __launch_bounds__(256)
+decode_rgb8_kernel(const uint8_t* __restrict__ in, __nv_bfloat16* __restrict__ out, long long rows,
+                   int W, int Wp, int wofs, float m0, float m1, float m2, float s0, float s1,
+                   float s2) {
+  const int quads = (Wp + 3) >> 2;
+  const long long total = rows * quads;
+  const float a0 = s0 * (1.f / 255.f), a1 = s1 * (1.f / 255.f), a2 = s2 * (1.f / 255.f);
+  const float b0 = -m0 * s0, b1 = -m1 * s1, b2 = -m2 * s2;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int qd = static_cast<int>(i % quads);
+    const long long row = i / quads;
+    const uint8_t* src = in + row * W * 3;
+    __nv_bfloat16* dst = out + (row * Wp + qd * 4) * 8;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int wp = qd * 4 + k;
+      if (wp >= Wp) break;
+      const int w = wp - wofs;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (w >= 0 && w < W) {
+        const uint8_t* p = src + w * 3;
+        const float r = static_cast<float>(p[0]) * a0 + b0;
+        const float g = static_cast<float>(p[1]) * a1 + b1;
+        const float b = static_cast<float>(p[2]) * a2 + b2;
+        v.x = pack_bf16x2(r, g);
+        v.y = pack_bf16x2(b, 0.f);
+      }
+      *reinterpret_cast<uint4*>(dst + k * 8) = v;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
@@ -681,6 +716,13 @@ cudaError_t softmax_xent(const void* logits, int logits_fp32, const int* labels,
 cudaError_t decode_normalize(const uint8_t* in, void* out, int N, int H, int W, int C, int Wp,
                              int Cp, int wofs, const float* mean3, const float* istd3,
                              cudaStream_t s) {
+  if (C == 3 && Cp == 8) {
+    const long long rows = static_cast<long long>(N) * H;
+    decode_rgb8_kernel<<<grid_for(rows * ((Wp + 3) / 4), 256, kMaxBlocks * 4), 256, 0, s>>>(
+        in, static_cast<__nv_bfloat16*>(out), rows, W, Wp, wofs, mean3[0], mean3[1], mean3[2],
+        istd3[0], istd3[1], istd3[2]);
+    TFOS_RET();
+  }
   const long long total = static_cast<long long>(N) * H * Wp;
   decode_normalize_kernel<<<grid_for(total, 256, kMaxBlocks * 4), 256, 0, s>>>(
       in, static_cast<__nv_bfloat16*>(out), N, H, W, C, Wp, Cp, wofs, mean3[0], mean3[1], mean3[2],

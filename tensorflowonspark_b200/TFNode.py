@@ -86,7 +86,7 @@ def start_cluster_server(ctx, num_gpus=1, rdma=False, backend=None, async_ps=Non
   return ctx.cluster_spec, ClusterServer(ctx, group=group)
 
 
-def export_saved_model(sess_or_model, export_dir, tag_set="serve", signatures=None):
+def export_saved_model(sess, export_dir, tag_set="serve", signatures=None):
   """Write an inference artefact to ``export_dir`` (weights + a JSON signature).
 
   The reference's version (TFNode.py:162-211) wrote a TF1 SavedModel from a session; here the
@@ -94,7 +94,7 @@ def export_saved_model(sess_or_model, export_dir, tag_set="serve", signatures=No
   ``signatures`` maps signature keys to ``{'inputs': {alias: tensor_name}, 'outputs': {...}}``.
   """
   from .utils import checkpoint
-  return checkpoint.export_model(sess_or_model, export_dir, tag_set=tag_set, signatures=signatures)
+  return checkpoint.export_model(sess, export_dir, tag_set=tag_set, signatures=signatures)
 
 
 def release_port(ctx):

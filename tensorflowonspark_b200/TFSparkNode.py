@@ -68,9 +68,9 @@ class TFNodeContext(object):
     """See :func:`TFNode.start_cluster_server`."""
     return TFNode.start_cluster_server(self, num_gpus, rdma, **kwargs)
 
-  def export_saved_model(self, model, export_dir, tag_set="serve", signatures=None):
-    """See :func:`TFNode.export_saved_model`."""
-    return TFNode.export_saved_model(model, export_dir, tag_set, signatures)
+  def export_saved_model(self, sess, export_dir, tag_set="serve", signatures=None):
+    """See :func:`TFNode.export_saved_model` (``sess``: the model; the name is the reference's)."""
+    return TFNode.export_saved_model(sess, export_dir, tag_set, signatures)
 
   def get_data_feed(self, train_mode=True, qname_in="input", qname_out="output", input_mapping=None):
     """A :class:`TFNode.DataFeed` bound to this node's manager."""

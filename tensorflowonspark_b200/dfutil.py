@@ -167,11 +167,11 @@ def _cast(base, v, binary):
   return v.decode("utf-8") if isinstance(v, (bytes, bytearray)) else v
 
 
-def fromTFExample(iterator, binary_features=[], schema=None):
+def fromTFExample(iter, binary_features=[], schema=None):  # noqa: A002 (reference arg name)
   """``mapPartitions`` function turning serialized Examples into Rows (fields sorted by name)."""
   out = []
   by_name = {f.name: f.dataType for f in schema.fields} if schema is not None else {}
-  for rec in iterator:
+  for rec in iter:
     if isinstance(rec, tuple):
       rec = rec[0]
     feats = tfrecord.decode_example(bytes(rec))
