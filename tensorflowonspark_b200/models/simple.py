@@ -37,6 +37,28 @@ def build_linear(state, in_features=2, out_features=1, input_name="x", output_na
   return _Served(m.to(dev).eval(), input_name, output_name, dev)
 
 
+class Echo(object):
+  """Serving callable that returns every named input under ``<prefix><name>`` - the type
+  plumbing of TFModel.transform can be tested end to end without a numeric model (the scenario
+  of the reference's Scala TFModelTest: batch2tensors / tensors2batch over 14 column types)."""
+
+  export_builder = "tensorflowonspark_b200.models.simple:build_echo"
+
+  def __init__(self, prefix="out_"):
+    self.prefix = prefix
+    self.export_builder_args = {"prefix": prefix}
+
+  def state_dict(self):
+    return {}
+
+  def __call__(self, **inputs):
+    return {self.prefix + k: v for k, v in inputs.items()}
+
+
+def build_echo(state, prefix="out_"):
+  return Echo(prefix)
+
+
 def allreduce_mean_grads(module, world_size):
   """Plain torch.distributed gradient averaging (the CPU/gloo plumbing path and the NCCL
   baseline; the B200 product path is parallel/fused_optim.py)."""

@@ -297,7 +297,11 @@ def _run_model(iterator, args, tf_args):
       assert t in outputs, "output tensor '{}' not produced by the model (have: {})".format(
           t, list(outputs))
       o = outputs[t]
-      o = o.detach().float().cpu().numpy() if hasattr(o, "detach") else np.asarray(o)
+      if hasattr(o, "detach"):   # torch tensor: keep integer / bool dtypes, widen half types
+        o = o.detach().cpu()
+        o = (o.float() if o.dtype.is_floating_point and o.element_size() < 4 else o).numpy()
+      else:
+        o = np.asarray(o)
       assert len(o) == len(tensors[0]), "output '{}' has {} rows, expected {}".format(
           t, len(o), len(tensors[0]))
       cols.append(o.tolist())

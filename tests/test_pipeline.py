@@ -120,3 +120,41 @@ def test_estimator_fit_export_transform(sc, spark, tmp_path):
        .setInputMapping({"c1": "x"}).setOutputMapping({"y": "cout"})
   pred = model.transform(test_df).head().cout[0]
   assert abs(pred - weights.sum()) < 0.05, pred
+
+
+def test_tfmodel_roundtrips_all_column_types(spark, tmp_path):
+  """Scenario of the reference's Scala TFModelTest (batch2tensors / tensors2batch, :18-128):
+  every supported column type travels DataFrame -> named input tensors -> model -> DataFrame
+  unchanged - scalars and 1-D arrays of bool / int / long / float / double / string / binary."""
+  from tensorflowonspark_b200 import pipeline
+  from tensorflowonspark_b200.models import simple
+  from tensorflowonspark_b200.utils import checkpoint
+  cols = {
+      "b": [True, False, True], "i": [1, -2, 3], "l": [2 ** 40, -5, 7], "f": [0.5, 1.5, -2.25],
+      "d": [1e-12, 2.0, 3.5], "s": ["x", "yy", "zzz"], "bin": [b"\x00\x01", b"ab", b""],
+      "ab": [[True, False], [False, False], [True, True]], "ai": [[1, 2], [3, 4], [5, 6]],
+      "af": [[0.5, 1.0], [1.5, 2.0], [2.5, 3.0]], "as": [["a", "b"], ["c", "d"], ["e", "f"]],
+  }
+  names = sorted(cols)
+  rows = [tuple(cols[n][r] for n in names) for r in range(3)]
+  df = spark.createDataFrame(rows, names)
+  export = str(tmp_path / "echo")
+  sig = {"serving_default": {"inputs": {n: n for n in names},
+                             "outputs": {"out_" + n: "out_" + n for n in names}}}
+  checkpoint.export_model(simple.Echo(), export, signatures=sig)
+  model = pipeline.TFModel({}).setExportDir(export).setBatchSize(2) \
+      .setInputMapping({n: n for n in names}) \
+      .setOutputMapping({"out_" + n: "res_" + n for n in names})
+  out = model.transform(df).collect()
+  assert len(out) == 3
+  for r, row in enumerate(out):
+    got = row.asDict() if hasattr(row, "asDict") else dict(zip(["res_" + n for n in names], row))
+    for n in names:
+      want = cols[n][r]
+      have = got["res_" + n]
+      if isinstance(want, float):
+        assert abs(have - want) < 1e-6 * max(1.0, abs(want)), (n, have, want)
+      elif isinstance(want, list) and want and isinstance(want[0], float):
+        assert all(abs(a - b) < 1e-6 for a, b in zip(have, want)), (n, have, want)
+      else:
+        assert have == want and type(have) is type(want), (n, have, want)

@@ -1,0 +1,68 @@
+"""Property tests (hypothesis): the Example codec and the shared-memory ring round-trip arbitrary
+well-formed inputs, and the native and pure-python codecs agree byte for byte."""
+import numpy as np
+import pytest
+
+hyp = pytest.importorskip("hypothesis")
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+from tensorflowonspark_b200 import shmring, tfrecord  # noqa: E402
+
+_names = st.text(alphabet="abcdefghijklmnopqrstuvwxyz_0123456789", min_size=1, max_size=12)
+_feature = st.one_of(
+    st.tuples(st.just("int64"), st.lists(st.integers(-2 ** 63, 2 ** 63 - 1), max_size=8)),
+    st.tuples(st.just("float"), st.lists(st.floats(width=32, allow_nan=False, allow_infinity=False),
+                                         max_size=8)),
+    st.tuples(st.just("bytes"), st.lists(st.binary(max_size=16), max_size=4)),
+)
+
+
+@settings(max_examples=150, deadline=None)
+@given(st.dictionaries(_names, _feature, max_size=6))
+def test_example_codec_roundtrip_and_native_python_agreement(features):
+  enc_py = tfrecord._py_encode(features)
+  assert tfrecord.encode_example(features) == enc_py          # native (if built) == python
+  for decode in (tfrecord.decode_example, tfrecord._py_decode):
+    got = decode(enc_py)
+    assert set(got) == set(features)
+    for k, (kind, vals) in features.items():
+      gk, gv = got[k]
+      if not vals:
+        assert list(gv) == []          # an empty list carries no type on the wire
+        continue
+      assert gk == kind
+      if kind == "float":
+        assert np.allclose(np.asarray(gv, np.float32), np.asarray(vals, np.float32), rtol=0, atol=0)
+      else:
+        assert list(gv) == list(vals)
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.lists(st.binary(max_size=64), max_size=10))
+def test_record_framing_roundtrip(tmp_path_factory, records):
+  path = str(tmp_path_factory.mktemp("tfr") / "part-00000")
+  tfrecord.write_records(path, records)
+  assert list(tfrecord.read_records(path)) == records
+
+
+_dtypes = st.sampled_from([np.uint8, np.int32, np.int64, np.float32, np.float64])
+
+
+@settings(max_examples=40, deadline=None)
+@given(st.integers(1, 40), st.lists(st.tuples(_dtypes, st.lists(st.integers(1, 5), max_size=3)),
+                                    min_size=1, max_size=3), st.integers(0, 2 ** 31 - 1))
+def test_ring_pack_unpack_roundtrip(nrows, colspecs, seed):
+  rng = np.random.RandomState(seed)
+  rows = [tuple((rng.randint(0, 100, size=shape)).astype(dt) for dt, shape in colspecs)
+          for _ in range(nrows)]
+  name, ring = shmring.create(2, 1 << 20)
+  try:
+    blk = shmring.pack_rows(ring, rows, timeout=1.0)
+    assert blk is not None and blk.nrows == nrows
+    cols = shmring.unpack_columns(ring, blk)
+    for j, (dt, shape) in enumerate(colspecs):
+      assert cols[j].dtype == np.dtype(dt) and cols[j].shape == (nrows,) + tuple(shape)
+      assert np.array_equal(cols[j], np.stack([r[j] for r in rows]))
+    ring.release_read(blk.pos)
+  finally:
+    shmring._unlink(name)
