@@ -118,6 +118,7 @@ int64_t plan_fwd(const py::dict& a, const py::dict& b, const py::dict& g, int bn
   f.out_fp32 = geti<int>(g, "out_fp32", 0);
   f.accumulate = geti<int>(g, "accumulate", 0);
   f.stem = geti<int>(g, "stem", 0);
+  f.acc_mask = reinterpret_cast<const uint8_t*>(geti<uint64_t>(g, "acc_mask", 0));
   f.bias = reinterpret_cast<const float*>(geti<uint64_t>(g, "bias", 0));
   f.col_sum = reinterpret_cast<float*>(geti<uint64_t>(g, "col_sum", 0));
   f.col_sumsq = reinterpret_cast<float*>(geti<uint64_t>(g, "col_sumsq", 0));

@@ -344,13 +344,18 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           // accumulate mode: the previous values do not depend on the MMA - issue all eight
           // 16-byte loads of this slab now so their latency overlaps the TMEM read + staging
           uint4 prev[8];
+          uint32_t pmask[8];
           if (acc_on) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int r2 = i * 4 + (lane >> 3);
               prev[i] = make_uint4(0u, 0u, 0u, 0u);
-              if ((vmask >> r2) & 1u)
-                prev[i] = *reinterpret_cast<const uint4*>(obase + roffs[i] + c * 64 + (lane & 7) * 8);
+              pmask[i] = 0xffu;
+              if ((vmask >> r2) & 1u) {
+                const long long e = roffs[i] + c * 64 + (lane & 7) * 8;
+                prev[i] = *reinterpret_cast<const uint4*>(obase + e);
+                if (a.acc_mask != nullptr) pmask[i] = a.acc_mask[e >> 3];
+              }
             }
           }
           uint32_t v[64];
@@ -428,8 +433,11 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                        n2 = unpack_bf16x2(val.z), n3 = unpack_bf16x2(val.w);
                 const float2 p0 = unpack_bf16x2(p.x), p1 = unpack_bf16x2(p.y),
                              p2 = unpack_bf16x2(p.z), p3 = unpack_bf16x2(p.w);
-                n0.x += p0.x, n0.y += p0.y, n1.x += p1.x, n1.y += p1.y;
-                n2.x += p2.x, n2.y += p2.y, n3.x += p3.x, n3.y += p3.y;
+                const uint32_t pm = pmask[i];   // bit j: element j of this 16-byte group counts
+                n0.x += (pm & 1u) ? p0.x : 0.f, n0.y += (pm & 2u) ? p0.y : 0.f;
+                n1.x += (pm & 4u) ? p1.x : 0.f, n1.y += (pm & 8u) ? p1.y : 0.f;
+                n2.x += (pm & 16u) ? p2.x : 0.f, n2.y += (pm & 32u) ? p2.y : 0.f;
+                n3.x += (pm & 64u) ? p3.x : 0.f, n3.y += (pm & 128u) ? p3.y : 0.f;
                 if (relu_on) {
                   n0.x = fmaxf(n0.x, 0.f), n0.y = fmaxf(n0.y, 0.f), n1.x = fmaxf(n1.x, 0.f);
                   n1.y = fmaxf(n1.y, 0.f), n2.x = fmaxf(n2.x, 0.f), n2.y = fmaxf(n2.y, 0.f);
@@ -642,6 +650,11 @@ IGemmPlan* igemm_plan_fwd(const TmapDesc& a, const TmapDesc& b, const FwdArgs& a
   const int rows = args.box_w * args.box_h * args.box_n;
   if (rows < 1 || rows > 128 || args.num_taps < 1 || args.num_taps > kMaxTaps) {
     snprintf(err, errlen, "bad box rows %d or taps %d", rows, args.num_taps);
+    return nullptr;
+  }
+  if (args.acc_mask != nullptr &&
+      (!args.accumulate || args.out_fp32 || (args.ldo & 7) != 0 || args.n_valid % bn != 0)) {
+    snprintf(err, errlen, "acc_mask needs accumulate, bf16 output and whole column tiles");
     return nullptr;
   }
   if (args.col_sum != nullptr && args.accumulate) {

@@ -46,6 +46,10 @@ struct FwdArgs {
   float* col_sum;           // optional fused per-column sum / sum of squares
   float* col_sumsq;         //   (batch-norm statistics of the stored tensor)
   void* out;
+  // accumulate mode only: one bit per element of ``out`` (layout [pixels, ldo / 8] bytes); the
+  // previous value takes part in the sum only where its bit is set.  This is the ReLU mask of a
+  // residual unit's output: dX = dgrad + mask * dY without a separate "masked dY" tensor.
+  const uint8_t* acc_mask;
   int b_resident, a_stages;  // set by igemm_plan_fwd: weight-stationary mode (igemm.cu)
   // stem mode (7x7/2 convolution on the window-row layout, see igemm.cu): ONE halo box of
   // 2*box_h+5 input rows per tile serves all seven filter rows; box_w must be 8

@@ -170,11 +170,7 @@ class BatchNorm(object):
     # element so that the backward pass does not have to re-read the whole bf16 output
     # (the buffer is never released: a captured CUDA graph may hold its address)
     if training and residual is not None and act == 1:
-      buf = getattr(self, "_mask_buf", None)
-      if buf is None or buf.numel() * 8 != x_raw.numel():
-        buf = self._mask_buf = torch.empty(x_raw.numel() // 8, dtype=torch.uint8,
-                                           device=x_raw.device)
-      self.mask = buf
+      self.mask = self.ensure_mask(x_raw.numel(), x_raw.device)
     else:
       self.mask = None
     if training:
@@ -188,12 +184,23 @@ class BatchNorm(object):
                                 self.scale, self.shift, self.eps)
     ops.K.bn_apply(x_raw, residual, self.scale, self.shift, y, act, self.mask)
 
-  def backward(self, dy, x_raw, y, dx, dres=None, relu=True, residual=False):
+  def ensure_mask(self, numel, device):
+    """The unit's ReLU bit mask buffer (numel / 8 bytes), allocated once."""
+    buf = getattr(self, "_mask_buf", None)
+    if buf is None or buf.numel() * 8 != numel:
+      buf = self._mask_buf = torch.empty(numel // 8, dtype=torch.uint8, device=device)
+    return buf
+
+  def backward(self, dy, x_raw, y, dx, dres=None, relu=True, residual=False, mask=None):
     """relu mask: recomputed from x_raw with the forward scale/shift when the unit has no
-    residual input (saves reading y: 2 of 6-8 bytes per element); from the stored y otherwise."""
+    residual input (saves reading y: 2 of 6-8 bytes per element); from the stored y otherwise;
+    ``mask``: another unit's bit mask (a projection shortcut's BN sees the gradient of the block
+    output, i.e. the ReLU that followed the *sum*)."""
     mode = 0 if not relu else (1 if (residual or dres is not None) else 2)
     ysrc = y if mode == 1 else None
-    if mode == 1 and getattr(self, "mask", None) is not None:
+    if mask is not None and relu:
+      mode, ysrc = 3, mask
+    elif mode == 1 and getattr(self, "mask", None) is not None:
       mode, ysrc = 3, self.mask   # bit mask written by forward(): 1/16 of y's bytes
     ops.K.bn_bwd_reduce(dy, x_raw, ysrc, self.mean, self.invstd, self.dgamma, self.dbeta, mode,
                         self.scale, self.shift)
@@ -217,7 +224,7 @@ class Conv(object):
             (W + 2 * self.pad - self.k) // self.stride + 1)
 
   def build(self, x, y, dy=None, dx=None, stats=None, relu=False, dx_accumulate=False,
-            need_dgrad=True, training=True):
+            need_dgrad=True, training=True, dx_acc_mask=None):
     st = self.store
     self.x, self.y = x, y
     if not training:
@@ -232,7 +239,7 @@ class Conv(object):
       self.wgrad = igemm.conv_wgrad(dy, x, st.g(self.sw), self.stride, self.pad)
       if need_dgrad and dx is not None:
         self.dgrad = igemm.conv_dgrad(dy, st.w(self.sw), dx, self.stride, self.pad,
-                                      accumulate=dx_accumulate)
+                                      accumulate=dx_accumulate, acc_mask=dx_acc_mask)
     self.dy = dy
 
   def forward(self):

@@ -120,8 +120,11 @@ class ResNetTrainer(object):
       for u in (b.u1, b.u2, b.u3) + ((b.ds,) if b.ds else ()):
         u.bn.build(dev)
       ident = b.ds is None
+      # the block output's ReLU mask (one bit per element, written by bn3's forward): identity
+      # blocks fold "mask * dY" into conv1's accumulating dgrad instead of materialising it
+      omask = b.u3.bn.ensure_mask(b.out.numel(), dev) if tr else None
       b.u1.conv.build(x, b.r1, b.g_r1, b.g_x, stats=b.u1.bn.stats, dx_accumulate=ident,
-                      training=tr)
+                      training=tr, dx_acc_mask=omask if ident else None)
       b.u2.conv.build(b.a1, b.r2, b.g_r2, b.g_a1, stats=b.u2.bn.stats, training=tr)
       b.u3.conv.build(b.a2, b.r3, b.g_r3, b.g_a2, stats=b.u3.bn.stats, training=tr)
       if b.ds is not None:
@@ -279,15 +282,16 @@ class ResNetTrainer(object):
     K.avgpool_bwd(self.g_avg, self.g_last)
     for bi in reversed(range(len(self.blocks))):
       b = self.blocks[bi]
-      # out = relu(bn3(r3) + idn): masked gradient goes to both branches
-      b.u3.bn.backward(b.g_out, b.r3, b.out, b.g_r3, dres=b.g_out, relu=True)
+      # out = relu(bn3(r3) + idn): the masked gradient goes to both branches; the mask is applied
+      # where g_out is consumed (here, in conv1's accumulate epilogue, in the shortcut's BN)
+      b.u3.bn.backward(b.g_out, b.r3, b.out, b.g_r3, relu=True, residual=True)
       b.u3.conv.backward()
       b.u2.bn.backward(b.g_a2, b.r2, b.a2, b.g_r2, relu=True)
       b.u2.conv.backward()
       b.u1.bn.backward(b.g_a1, b.r1, b.a1, b.g_r1, relu=True)
       b.u1.conv.backward()  # writes (ds) or accumulates (identity) into g_x
       if b.ds is not None:
-        b.ds.bn.backward(b.g_out, b.rd, None, b.g_rd, relu=False)
+        b.ds.bn.backward(b.g_out, b.rd, None, b.g_rd, relu=True, mask=b.u3.bn.mask)
         b.ds.conv.backward()  # accumulates into g_x
       self.optim.launch(bi)   # buckets that became final start their all-reduce now
     K.maxpool_bwd(self.g_pool, self.pool_idx, self.g_stem_act, 3, 2, 1)

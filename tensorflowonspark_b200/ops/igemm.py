@@ -209,7 +209,8 @@ def conv_fprop(x, w, y, stride=1, pad=0, bias=None, relu=False, stats=None):
       R, S, stride, Cin, Cout, OH, OW))
 
 
-def conv_dgrad(dy, w, dx, stride=1, pad=0, accumulate=False, relu=False, bias=None, stats=None):
+def conv_dgrad(dy, w, dx, stride=1, pad=0, accumulate=False, relu=False, bias=None, stats=None,
+               acc_mask=None):
   """dx[N,H,W,Cin] (=|+=) conv_transpose(dy[N,OH,OW,Cout], w[Cout,R,S,Cin]).
 
   Also the forward of a transposed convolution (Keras Conv2DTranspose) when
@@ -246,11 +247,12 @@ def conv_dgrad(dy, w, dx, stride=1, pad=0, accumulate=False, relu=False, bias=No
         "lim_w": cw, "lim_h": ch, "lim_n": N, "OW": W, "OH": H,
         "osw": stride, "oow": pw, "osh": stride, "ooh": ph,
         "ldo": Cin, "n_valid": Cin, "accumulate": int(accumulate), "relu": int(relu),
+        "acc_mask": acc_mask.data_ptr() if acc_mask is not None else 0,
         "bias": bias.data_ptr() if bias is not None else 0, "out": dx.data_ptr(),
     }
     _stats_args(g, stats)  # transposed-conv *forward* feeding a batch norm
     handles.append(_C().igemm_plan_fwd(ta, tb, g, bn, True))
-  return Plan(handles, (dy, w, dx, bias, stats), "dgrad {}x{} s{} {}->{} @{}x{}".format(
+  return Plan(handles, (dy, w, dx, bias, stats, acc_mask), "dgrad {}x{} s{} {}->{} @{}x{}".format(
       R, S, stride, Cout, Cin, H, W))
 
 

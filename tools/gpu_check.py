@@ -176,6 +176,33 @@ def conv_dgrad():
 
 
 @check
+def dgrad_masked_accumulate():
+  """dx = dgrad(dy) + mask * dx_prev with the mask given as one bit per element (the ReLU mask of
+  a residual unit, models/resnet.py): the accumulate epilogue applies it to the value it re-reads."""
+  import torch
+  from tensorflowonspark_b200.ops import igemm
+  ok = True
+  for case in [(4, 28, 28, 256, 64, 1, 1), (16, 56, 56, 256, 64, 1, 1), (2, 14, 14, 128, 128, 3, 1)]:
+    N, H, W, Ci, Co, k, stride = case
+    x, w, OH, OW, pad = _conv_case(*case)
+    dy = torch.randn(N, OH, OW, Co, device="cuda").bfloat16()
+    xr = x.float().requires_grad_(True)
+    _conv_ref(xr, w, stride, pad).backward(dy.float())
+    base = torch.randn_like(x)
+    keep = torch.rand(N, H, W, Ci, device="cuda") > 0.4
+    bits = torch.zeros(N * H * W * Ci // 8, dtype=torch.uint8, device="cuda")
+    k8 = keep.reshape(-1, 8).to(torch.uint8)
+    for j in range(8):
+      bits |= k8[:, j] << j
+    dx = base.clone()
+    igemm.conv_dgrad(dy, w, dx, stride, pad, accumulate=True, acc_mask=bits).run()
+    torch.cuda.synchronize()
+    ref = xr.grad + base.float() * keep.float()
+    ok &= _report("dgrad+masked acc {}".format(case), _rel(dx, ref), 3e-2)
+  return ok
+
+
+@check
 def conv_wgrad():
   import torch
   from tensorflowonspark_b200.ops import igemm
