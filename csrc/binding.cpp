@@ -220,6 +220,34 @@ void bn_apply(const Tensor& x, c10::optional<Tensor> residual, const Tensor& sca
                        act, cur_stream()),
         "bn_apply");
 }
+void bn_apply_finalize(const Tensor& x, c10::optional<Tensor> residual, Tensor y, int act,
+                       c10::optional<Tensor> mask, const Tensor& sum, const Tensor& sumsq,
+                       const Tensor& gamma, const Tensor& beta, c10::optional<Tensor> running_mean,
+                       c10::optional<Tensor> running_var, Tensor mean, Tensor invstd, Tensor scale,
+                       Tensor shift, double count, double eps, double momentum) {
+  need(x, torch::kBFloat16, "x");
+  need(y, torch::kBFloat16, "y");
+  const int C = x.size(-1);
+  TORCH_CHECK(C % 8 == 0 && sum.numel() == C && sumsq.numel() == C, "bn_apply_finalize: C");
+  tfos::BnFinalize f;
+  f.sum = sum.data_ptr<float>();
+  f.sumsq = sumsq.data_ptr<float>();
+  f.gamma = gamma.data_ptr<float>();
+  f.beta = beta.data_ptr<float>();
+  f.running_mean = running_mean.has_value() ? running_mean->data_ptr<float>() : nullptr;
+  f.running_var = running_var.has_value() ? running_var->data_ptr<float>() : nullptr;
+  f.mean = mean.data_ptr<float>();
+  f.invstd = invstd.data_ptr<float>();
+  f.scale = scale.data_ptr<float>();
+  f.shift = shift.data_ptr<float>();
+  f.count = static_cast<float>(count);
+  f.eps = static_cast<float>(eps);
+  f.momentum = static_cast<float>(momentum);
+  check(tfos::bn_apply_finalize(x.data_ptr(), optptr(residual), y.data_ptr(),
+                                mask.has_value() ? mask->data_ptr<uint8_t>() : nullptr,
+                                x.numel() / C, C, act, f, cur_stream()),
+        "bn_apply_finalize");
+}
 void bn_bwd_reduce(const Tensor& dy, const Tensor& x, c10::optional<Tensor> y, const Tensor& mean,
                    const Tensor& invstd, Tensor dgamma, Tensor dbeta, int relu,
                    c10::optional<Tensor> fscale, c10::optional<Tensor> fshift) {
@@ -503,6 +531,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("bn_inference_coeffs", &bn_inference_coeffs);
   m.def("bn_apply", &bn_apply, py::arg("x"), py::arg("residual"), py::arg("scale"),
         py::arg("shift"), py::arg("y"), py::arg("act"), py::arg("mask") = py::none());
+  m.def("bn_apply_finalize", &bn_apply_finalize);
   m.def("bn_bwd_reduce", &bn_bwd_reduce);
   m.def("bn_bwd_apply", &bn_bwd_apply);
   m.def("add_act", &add_act);

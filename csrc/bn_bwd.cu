@@ -230,11 +230,12 @@ bn_bwd_apply_kernel(const __nv_bfloat16* dy, const __nv_bfloat16* __restrict__ x
 // Same thread geometry as the backward kernels (a thread keeps one 8-channel group, so scale /
 // shift are loaded once, and four rows are in flight); the arithmetic runs on the packed
 // fp32x2 pipe.  mask (optional): one bit per element, set where the pre-activation is > 0.
+template <bool FIN>
 __global__ void __launch_bounds__(kThreads, 3)
 bn_fwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ residual,
                     const float* __restrict__ scale, const float* __restrict__ shift,
                     __nv_bfloat16* __restrict__ y, uint8_t* __restrict__ mask, long long P, int C,
-                    int act) {
+                    int act, const BnFinalize fin) {
   const Geo G = geo(C);
   if (G.r_in >= G.rl) return;
   const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
@@ -244,10 +245,41 @@ bn_fwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __
     if (g >= G.groups) continue;
     const int c = g * 8;
     float2 sc[4], sh[4];
+    if (FIN) {
+      const bool writer = blockIdx.x == 0 && G.r_in == 0;   // one thread per channel group
+      float s8[8], h8[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      sc[j] = make_float2(scale[c + 2 * j], scale[c + 2 * j + 1]);
-      sh[j] = make_float2(shift[c + 2 * j], shift[c + 2 * j + 1]);
+      for (int j = 0; j < 8; ++j) {
+        const int ch = c + j;
+        const float m = fin.sum[ch] / fin.count;
+        const float var = fmaxf(fin.sumsq[ch] / fin.count - m * m, 0.f);
+        const float is = rsqrtf(var + fin.eps);
+        s8[j] = fin.gamma[ch] * is;
+        h8[j] = fin.beta[ch] - m * s8[j];
+        if (writer) {
+          fin.mean[ch] = m;
+          fin.invstd[ch] = is;
+          fin.scale[ch] = s8[j];
+          fin.shift[ch] = h8[j];
+          if (fin.running_mean != nullptr) {
+            const float unbiased = fin.count > 1.f ? var * fin.count / (fin.count - 1.f) : var;
+            fin.running_mean[ch] = (1.f - fin.momentum) * fin.running_mean[ch] + fin.momentum * m;
+            fin.running_var[ch] =
+                (1.f - fin.momentum) * fin.running_var[ch] + fin.momentum * unbiased;
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        sc[j] = make_float2(s8[2 * j], s8[2 * j + 1]);
+        sh[j] = make_float2(h8[2 * j], h8[2 * j + 1]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        sc[j] = make_float2(scale[c + 2 * j], scale[c + 2 * j + 1]);
+        sh[j] = make_float2(shift[c + 2 * j], shift[c + 2 * j + 1]);
+      }
     }
     const long long stride = static_cast<long long>(gridDim.x) * G.rl;
     for (long long p = static_cast<long long>(blockIdx.x) * G.rl + G.r_in; p < P;
@@ -313,9 +345,18 @@ inline int env_waves(const char* name, int dflt) {
 cudaError_t bn_apply(const void* x, const void* residual, const float* scale, const float* shift,
                      void* y, uint8_t* mask, long long P, int C, int act, cudaStream_t s) {
   static const int waves = env_waves("TFOS_BN_WAVES_FWD", 3);
-  bn_fwd_apply_kernel<<<red_grid(P, C, waves), kThreads, 0, s>>>(
+  bn_fwd_apply_kernel<false><<<red_grid(P, C, waves), kThreads, 0, s>>>(
       static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(residual), scale,
-      shift, static_cast<__nv_bfloat16*>(y), mask, P, C, act);
+      shift, static_cast<__nv_bfloat16*>(y), mask, P, C, act, BnFinalize());
+  return cudaGetLastError();
+}
+
+cudaError_t bn_apply_finalize(const void* x, const void* residual, void* y, uint8_t* mask,
+                              long long P, int C, int act, const BnFinalize& fin, cudaStream_t s) {
+  static const int waves = env_waves("TFOS_BN_WAVES_FWD", 3);
+  bn_fwd_apply_kernel<true><<<red_grid(P, C, waves), kThreads, 0, s>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(residual), nullptr,
+      nullptr, static_cast<__nv_bfloat16*>(y), mask, P, C, act, fin);
   return cudaGetLastError();
 }
 

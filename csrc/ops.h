@@ -20,6 +20,26 @@ cudaError_t bn_inference_coeffs(const float* gamma, const float* beta, const flo
 // mask (optional): one bit per element, set where the pre-activation value is > 0
 cudaError_t bn_apply(const void* x, const void* residual, const float* scale, const float* shift,
                      void* y, uint8_t* mask, long long P, int C, int act, cudaStream_t s);
+// Same, with the statistics finalisation folded in: every thread derives scale / shift of its
+// channel group from the accumulated (sum, sumsq); one designated thread per group also stores
+// mean / invstd / scale / shift (the backward kernels read them) and updates the running
+// statistics.  The sums are NOT cleared here (other blocks are still reading them): the trainer
+// zeroes its whole statistics arena once per step.
+struct BnFinalize {
+  const float* sum;
+  const float* sumsq;
+  const float* gamma;
+  const float* beta;
+  float* running_mean;
+  float* running_var;
+  float* mean;
+  float* invstd;
+  float* scale;
+  float* shift;
+  float count, eps, momentum;
+};
+cudaError_t bn_apply_finalize(const void* x, const void* residual, void* y, uint8_t* mask,
+                              long long P, int C, int act, const BnFinalize& fin, cudaStream_t s);
 cudaError_t bn_bwd_reduce(const void* dy, const void* x, const void* y, const float* mean,
                           const float* invstd, const float* fscale, const float* fshift,
                           long long P, int C, int relu, float* dgamma, float* dbeta,

@@ -87,8 +87,12 @@ class ResNetTrainer(object):
     PH, PW = (OH + 2 - 3) // 2 + 1, (OW + 2 - 3) // 2 + 1
     self.pool = _buf((B, PH, PW, 64), dev)
     self.pool_idx = _buf((B, PH, PW, 64), dev, torch.uint8)
-    self.stem_bn.build(dev)
     tr = training
+    # all batch-norm statistics accumulators live in one arena that is zeroed once per step;
+    # finalisation is folded into the apply kernels (engine.BatchNorm.build)
+    self.stats_arena = engine.StatsArena(dev) if (tr and dev.type == "cuda" and os.environ.get(
+        "TFOS_BN_FUSED_FINALIZE", "1") != "0") else None
+    self.stem_bn.build(dev, self.stats_arena)
     self.p_stem = igemm.stem_fprop(self.xp, st.w(self.stem_w), self.stem_raw,
                                    stats=self.stem_bn.stats if tr else None)
     if tr:
@@ -118,7 +122,7 @@ class ResNetTrainer(object):
       else:
         b.g_r1 = b.g_a1 = b.g_r2 = b.g_a2 = b.g_r3 = b.g_out = b.g_x = None
       for u in (b.u1, b.u2, b.u3) + ((b.ds,) if b.ds else ()):
-        u.bn.build(dev)
+        u.bn.build(dev, self.stats_arena)
       ident = b.ds is None
       # the block output's ReLU mask (one bit per element, written by bn3's forward): identity
       # blocks fold "mask * dY" into conv1's accumulating dgrad instead of materialising it
@@ -242,6 +246,8 @@ class ResNetTrainer(object):
   def _forward(self, training, remote=False):
     K = ops.K
     run = (lambda c: c.forward_remote()) if remote else (lambda c: c.forward())
+    if self.stats_arena is not None:
+      self.stats_arena.zero()   # the fused conv epilogues accumulate from zero every pass
     K.decode_normalize(self.in_u8, self.xp, igemm.STEM_PAD, self.mean, self.std)
     (self.p_stem_remote if remote else self.p_stem).run()
     self.stem_bn.forward(self.stem_raw, self.stem_act, None, 1, training)

@@ -339,6 +339,21 @@ def batchnorm():
       ok &= _report("bn bitmask dgamma", _rel(d3, dgamma), 1e-5)
       ok &= _report("bn bitmask dx", _rel(dx3, dx), 2e-3)  # dgamma: atomic order
       ok &= _report("bn bitmask dres", _rel(dres3, dres), 1e-9)
+    # finalisation folded into the apply kernel == bn_finalize + bn_apply
+    if C % 8 == 0:
+      s2, ss2 = z(), z()
+      K.bn_stats(x, s2, ss2)
+      m2, is2, sc2, sh2, rm2, rv2 = z(), z(), z(), z(), z(), z() + 1
+      y4 = torch.empty_like(x)
+      K.bn_apply_finalize(x, res, y4, 1, None, s2, ss2, gamma, beta, rm2, rv2, m2, is2, sc2, sh2,
+                          float(P), 1e-5, 0.1)
+      torch.cuda.synchronize()
+      # (the two runs sum the statistics with atomics in different orders: last-bit differences
+      # in the mean, hence the odd bf16 rounding flip in y)
+      ok &= _report("bn fused finalize: y", _rel(y4, y), 1e-2)
+      ok &= _report("bn fused finalize: mean/invstd", _rel(m2, mean) + _rel(is2, invstd), 1e-5)
+      ok &= _report("bn fused finalize: scale/shift", _rel(sc2, scale) + _rel(sh2, shift), 1e-5)
+      ok &= _report("bn fused finalize: running stats", _rel(rm2, rm) + _rel(rv2, rv), 1e-5)
     # no-residual unit: ReLU mask recomputed from x (mode 2) must match the stored-y mask (mode 1)
     y2 = torch.empty_like(x)
     K.bn_apply(x, None, scale, shift, y2, 1)
