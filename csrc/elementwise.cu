@@ -251,6 +251,58 @@ maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restric
   }
 }
 
+// 3x3 / stride 2 / pad 1 with a 2-D thread tile: a block covers 8 x 4 output pixels x 8 channel
+// groups (C = 64: one block per tile; wider C: blockIdx.y walks the channel groups), so the 3x3
+// windows of neighbouring outputs - which share 5 of 9 input pixels - hit in L1 instead of
+// pulling every input pixel 2.25 times through the L2 -> SM fabric (row-major thread order put
+// the vertical neighbours in different blocks).
+__global__ void __launch_bounds__(256)
+maxpool_fwd_3x3s2_tiled_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                               uint8_t* __restrict__ idx, int N, int H, int W, int C, int OH,
+                               int OW) {
+  const int tiles_w = (OW + 7) >> 3, tiles_h = (OH + 3) >> 2;
+  int t = blockIdx.x;
+  const int tw = t % tiles_w;
+  t /= tiles_w;
+  const int th = t % tiles_h;
+  const int n = t / tiles_h;
+  const int g = blockIdx.y * 8 + (threadIdx.x & 7);
+  const int ow = tw * 8 + ((threadIdx.x >> 3) & 7);
+  const int oh = th * 4 + (threadIdx.x >> 6);
+  if (ow >= OW || oh >= OH || g * 8 >= C) return;
+  float best[8];
+  int bi[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) best[j] = -INFINITY, bi[j] = 0;
+  uint4 raw[9];
+  bool ok[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const int h = oh * 2 - 1 + k / 3, w = ow * 2 - 1 + k % 3;
+    ok[k] = h >= 0 && h < H && w >= 0 && w < W;
+    raw[k] = make_uint4(0u, 0u, 0u, 0u);
+    if (ok[k]) raw[k] = ld_nc_v4(x + ((static_cast<long long>(n) * H + h) * W + w) * C + g * 8);
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    if (!ok[k]) continue;
+    const uint32_t wd[4] = {raw[k].x, raw[k].y, raw[k].z, raw[k].w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float f = __uint_as_float((j & 1) ? (wd[j >> 1] & 0xffff0000u) : (wd[j >> 1] << 16));
+      if (f > best[j]) best[j] = f, bi[j] = k;
+    }
+  }
+  const long long o = ((static_cast<long long>(n) * OH + oh) * OW + ow) * C + g * 8;
+  store8(y + o, best);
+  if (idx != nullptr) {
+    uint2 p;
+    p.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
+    p.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
+    *reinterpret_cast<uint2*>(idx + o) = p;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx,
                    __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C, int OH, int OW,
@@ -296,15 +348,22 @@ maxpool_bwd_3x3s2_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __
                          int OW) {
   const int groups = C >> 3;
   const int BH = (H + 1) >> 1, BW = (W + 1) >> 1;
-  const long long total = static_cast<long long>(N) * BH * BW * groups;
+  // thread order: channel group, then an 8 x 4 tile of 2x2 blocks, then tiles - neighbouring
+  // blocks (which share their pooling windows) sit in the same thread block and hit in L1
+  const int tiles_w = (BW + 7) >> 3, tiles_h = (BH + 3) >> 2;
+  const long long total = static_cast<long long>(N) * tiles_h * tiles_w * 32 * groups;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int g = static_cast<int>(i % groups);
     long long r = i / groups;
-    const int bw = static_cast<int>(r % BW);
-    r /= BW;
-    const int bh = static_cast<int>(r % BH);
-    const int n = static_cast<int>(r / BH);
+    const int pw = static_cast<int>(r & 7);
+    const int ph = static_cast<int>((r >> 3) & 3);
+    r >>= 5;
+    const int bw = static_cast<int>(r % tiles_w) * 8 + pw;
+    r /= tiles_w;
+    const int bh = static_cast<int>(r % tiles_h) * 4 + ph;
+    const int n = static_cast<int>(r / tiles_h);
+    if (bw >= BW || bh >= BH) continue;
     uint4 gq[4];
     uint2 iq[4];
 #pragma unroll
@@ -663,11 +722,19 @@ cudaError_t colsum(const void* x, long long P, int C, float* out, cudaStream_t s
 cudaError_t maxpool_fwd(const void* x, void* y, uint8_t* idx, int N, int H, int W, int C, int OH,
                         int OW, int k, int stride, int pad, cudaStream_t s) {
   const long long total = static_cast<long long>(N) * OH * OW * (C >> 3);
-  if (k == 3 && stride == 2 && pad == 1)
+  if (k == 3 && stride == 2 && pad == 1) {
+    const long long tiles = static_cast<long long>(N) * ((OH + 3) / 4) * ((OW + 7) / 8);
+    const int gy = ((C >> 3) + 7) / 8;
+    if (tiles <= 0x7fffffffLL && gy <= 65535) {
+      maxpool_fwd_3x3s2_tiled_kernel<<<dim3(static_cast<unsigned>(tiles), gy), 256, 0, s>>>(
+          static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), idx, N, H, W, C,
+          OH, OW);
+      TFOS_RET();
+    }
     maxpool_fwd_kernel<3, 2, 1><<<grid_for(total, 256, kMaxBlocks * 4), 256, 0, s>>>(
         static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), idx, N, H, W, C, OH,
         OW, k, stride, pad);
-  else
+  } else
     maxpool_fwd_kernel<0, 0, 0><<<grid_for(total, 256, kMaxBlocks * 4), 256, 0, s>>>(
         static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), idx, N, H, W, C, OH,
         OW, k, stride, pad);
@@ -676,7 +743,8 @@ cudaError_t maxpool_fwd(const void* x, void* y, uint8_t* idx, int N, int H, int 
 cudaError_t maxpool_bwd(const void* dy, const uint8_t* idx, void* dx, int N, int H, int W, int C,
                         int OH, int OW, int k, int stride, int pad, cudaStream_t s) {
   if (k == 3 && stride == 2 && pad == 1) {
-    const long long blocks = static_cast<long long>(N) * ((H + 1) / 2) * ((W + 1) / 2) * (C >> 3);
+    const long long blocks = static_cast<long long>(N) * (((H + 1) / 2 + 3) / 4) *
+                             (((W + 1) / 2 + 7) / 8) * 32 * (C >> 3);
     maxpool_bwd_3x3s2_kernel<<<grid_for(blocks, 256, kMaxBlocks * 4), 256, 0, s>>>(
         static_cast<const __nv_bfloat16*>(dy), idx, static_cast<__nv_bfloat16*>(dx), N, H, W, C,
         OH, OW);
