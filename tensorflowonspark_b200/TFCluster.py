@@ -6,8 +6,6 @@ a "node" is differs: each Spark executor hosts one PyTorch rank bound to one B20
 TFSparkNode.py) and the gradient / broadcast / parameter-server traffic runs through the
 sm_100a kernels in csrc/optim_comm.cu instead of TensorFlow's runtime.
 """
-from __future__ import absolute_import, division, print_function
-
 import logging
 import os
 import random

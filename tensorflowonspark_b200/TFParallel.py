@@ -6,8 +6,6 @@ can take its own slot of the host's GPUs; the function receives a bare ``TFNodeC
 ``worker_num`` / ``executor_id`` / ``num_workers`` / ``defaultFS`` and shards its own input
 (reference examples/mnist/keras/mnist_inference.py:41-45).
 """
-from __future__ import absolute_import, division, print_function
-
 import logging
 
 from . import TFSparkNode, util

@@ -12,8 +12,6 @@ API and life-cycle parity with tensorflowonspark/TFSparkNode.py (``run`` / ``tra
 * InputMode.SPARK rows travel as blocks through a shared-memory pinned ring (shmring.py) or as
   chunked queue items - never one pickled RPC per row (reference hot loops :500-502, :561-563).
 """
-from __future__ import absolute_import, division, print_function
-
 import json
 import logging
 import multiprocessing

@@ -6,8 +6,6 @@ side (DFUtil.scala:21-259: schema *hints*; SimpleTypeParser.scala:27-64: the
 ``struct<name:type,...>`` grammar, here :func:`parse_schema`).  Records are framed and the
 ``tf.train.Example`` protos are encoded by the native codec in csrc/tfrecord.cc.
 """
-from __future__ import absolute_import, division, print_function
-
 import logging
 import os
 import re

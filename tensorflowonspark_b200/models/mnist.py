@@ -12,7 +12,6 @@ Two implementations with identical parameters:
 import torch
 
 from .. import ops
-from ..ops import igemm
 from .engine import Dense, ParamStore, constant, he_normal
 
 

@@ -12,7 +12,6 @@ Layout conventions (all bf16 unless noted):
 These replace the cuDNN/cuBLAS calls the reference reaches through TensorFlow
 (SURVEY.md section 2.6(b)).
 """
-import math
 import os
 
 from .. import _build

@@ -9,8 +9,6 @@ framework's export artefact (utils/checkpoint.py: weights + JSON signature) wher
 reference loaded a TensorFlow SavedModel; ``signature_def_key`` / ``tag_set`` / the input and
 output mappings keep their meaning.
 """
-from __future__ import absolute_import, division, print_function
-
 import argparse
 import copy
 import logging

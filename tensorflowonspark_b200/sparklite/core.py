@@ -23,10 +23,8 @@ import os
 import shutil
 import signal
 import socket
-import sys
 import tempfile
 import threading
-import time
 import traceback
 import uuid
 

@@ -1,6 +1,4 @@
 """Host utilities (reference: tensorflowonspark/util.py:21-94)."""
-from __future__ import absolute_import, division, print_function
-
 import errno
 import logging
 import os
