@@ -9,6 +9,14 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
+def _free_port():
+  """A port nobody listens on right now (fixed rendezvous ports collide with leftovers)."""
+  import socket
+  with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as sk:
+    sk.bind(("127.0.0.1", 0))
+    return str(sk.getsockname()[1])
+
+
 def test_fused_collectives_two_ranks():
   import torch
   if torch.cuda.device_count() < 2:
@@ -16,7 +24,7 @@ def test_fused_collectives_two_ranks():
   root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
   env = dict(os.environ, TFOS_FULL="0")
   p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node",
-                      "2", "--master-addr", "127.0.0.1", "--master-port", "29533",
+                      "2", "--master-addr", "127.0.0.1", "--master-port", _free_port(),
                       os.path.join(root, "tools", "gpu_check_multi.py")],
                      capture_output=True, text=True, timeout=600, env=env, cwd=root)
   print(p.stdout[-4000:], p.stderr[-2000:])
@@ -33,7 +41,7 @@ def test_lockstep_and_replica_consistency_under_cuda_graphs(model):
     pytest.skip("needs 2 GPUs")
   root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
   p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node",
-                      "2", "--master-addr", "127.0.0.1", "--master-port", "29534",
+                      "2", "--master-addr", "127.0.0.1", "--master-port", _free_port(),
                       os.path.join(root, "tools", "lockstep_check.py"), model],
                      capture_output=True, text=True, timeout=600, cwd=root)
   print(p.stdout[-3000:], p.stderr[-2000:])
