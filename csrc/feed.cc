@@ -11,6 +11,7 @@
 #include <chrono>
 #include <cstdint>
 #include <cstring>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <thread>
@@ -79,18 +80,23 @@ class ShmRing {
       // First-touch page faults of a fresh tmpfs mapping cost ~0.5 s per 64 MiB here - far more
       // than the memcpy that fills a slot.  Populate the payload pages in the background
       // (MADV_POPULATE_WRITE allocates without modifying contents, so it may race with feeders).
+      // Detached, with a shared stop flag: the owner may be destroyed - or the process forked
+      // (node processes are forked from the executor that created the ring; a std::thread copied
+      // into a child must never be joined) - while the population is still running.
       uint8_t* p = base_ + data_off;
       const uint64_t n = slot_bytes * nslots;
-      populate_ = std::thread([p, n]() {
+      stop_populate_ = std::make_shared<std::atomic<bool>>(false);
+      std::shared_ptr<std::atomic<bool>> stop = stop_populate_;
+      std::thread([p, n, stop]() {
 #ifdef MADV_POPULATE_WRITE
-        const uint64_t step = 8ull << 20;
-        for (uint64_t o = 0; o < n; o += step)
+        const uint64_t step = 4ull << 20;
+        for (uint64_t o = 0; o < n && !stop->load(); o += step)
           if (madvise(p + o, (n - o < step) ? n - o : step, MADV_POPULATE_WRITE) != 0) break;
 #else
         (void)p;
         (void)n;
 #endif
-      });
+      }).detach();
     } else {
       fd = shm_open(name.c_str(), O_RDWR, 0600);
       if (fd < 0) throw std::runtime_error("shm_open(attach) failed for " + name);
@@ -109,7 +115,7 @@ class ShmRing {
     }
   }
   ~ShmRing() {
-    if (populate_.joinable()) populate_.join();
+    if (stop_populate_) stop_populate_->store(true);
     if (pinned_) cudaHostUnregister(base_);
     if (base_ && base_ != MAP_FAILED) munmap(base_, size_);
     if (owner_) shm_unlink(name_.c_str());
@@ -199,7 +205,7 @@ class ShmRing {
   Header* hdr_ = nullptr;
   SlotMeta* slots_ = nullptr;
   bool pinned_ = false;
-  std::thread populate_;
+  std::shared_ptr<std::atomic<bool>> stop_populate_;
 };
 
 }  // namespace
