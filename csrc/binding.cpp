@@ -155,6 +155,16 @@ int64_t plan_wgrad(const py::dict& a, const py::dict& b, const py::dict& g, int 
   w.n_valid = geti<int>(g, "n_valid", 0);
   w.ldw = geti<int>(g, "ldw", 0);
   w.stem = geti<int>(g, "stem", 0);
+  w.halo_boxes = geti<int>(g, "halo_boxes", 1);
+  w.halo_rows = geti<int>(g, "halo_rows", 21);
+  w.halo_hmul = geti<int>(g, "halo_hmul", 2);
+  w.halo_h0 = geti<int>(g, "halo_h0", 0);
+  w.halo_jmul = geti<int>(g, "halo_jmul", 2);
+  w.halo_rowbytes = geti<int>(g, "halo_rowbytes", 2048);
+  w.halo_nacc = geti<int>(g, "halo_nacc", 7);
+  fill_ints(g, "acc_box", w.acc_box, tfos::kMaxTaps);
+  fill_ints(g, "acc_row", w.acc_row, tfos::kMaxTaps);
+  fill_ints(g, "box_dw", w.box_dw, 3);
   w.wide = geti<int>(g, "wide", 0);
   w.dw = reinterpret_cast<float*>(geti<uint64_t>(g, "dw", 0));
   TORCH_CHECK(w.dw != nullptr && w.ldw > 0, "igemm wgrad: dw/ldw");

@@ -214,15 +214,13 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t a_base = smem_u32(ring + stage * stage_stride);
+          const uint64_t ad0 = umma_desc_sw128(a_base, 16, 2 * kStemBoxW * 128);
+          const uint64_t bd0 = umma_desc_sw128(smem_u32(smem), 16, 1024);
           for (int r = 0; r < 7; ++r) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t adesc =
-                  umma_desc_sw128(a_base + r * (kStemBoxW * 128) + k * 32, 16, 2 * kStemBoxW * 128);
-              const uint64_t bdesc =
-                  umma_desc_sw128(smem_u32(smem + r * Cfg::kBBytes) + k * 32, 16, 1024);
-              umma_bf16(d_tmem, adesc, bdesc, idesc, (r | k) != 0 ? 1u : 0u);
-            }
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(d_tmem, ad0 + r * ((kStemBoxW * 128) >> 4) + k * 2,
+                        bd0 + r * (Cfg::kBBytes >> 4) + k * 2, idesc, (r | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty[stage]);
           if (++stage == nstages) {
@@ -236,13 +234,14 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t a_base = smem_u32(ring + stage * stage_stride);
           const uint32_t b_base =
               resident ? smem_u32(smem + it * Cfg::kBBytes) : a_base + kABytes;
+          // descriptors advance by 64-bit adds (start address = low field, 16-byte units)
+          const uint64_t ad0 = umma_desc_sw128(a_base, 16, 1024);
+          const uint64_t bd0 =
+              B_MN ? umma_desc_sw128(b_base, 8192, 1024) : umma_desc_sw128(b_base, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t adesc = umma_desc_sw128(a_base + k * 32, 16, 1024);
-            const uint64_t bdesc = B_MN ? umma_desc_sw128(b_base + k * 2048, 8192, 1024)
-                                        : umma_desc_sw128(b_base + k * 32, 16, 1024);
-            umma_bf16(d_tmem, adesc, bdesc, idesc, (it | k) != 0 ? 1u : 0u);
-          }
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(d_tmem, ad0 + k * 2, bd0 + k * (B_MN ? 128 : 2), idesc,
+                      (it | k) != 0 ? 1u : 0u);
           umma_commit(&empty[stage]);
           if (++stage == nstages) {
             stage = 0;
@@ -743,13 +742,19 @@ IGemmPlan* igemm_plan_wgrad(const TmapDesc& a, const TmapDesc& b, const WgradArg
     }
     p->total_work = args.num_taps * ((args.m_tiles + 1) / 2) * args.n_tiles * args.k_splits;
   }
-  if (args.stem) {  // igemm_wgrad_stem_kernel: all seven filter rows in one work item
-    if (bn != 64 || args.box_w != 16 || args.box_h != 8 || args.box_n != 1 || args.m_valid > 64 ||
-        args.m_tiles != 1 || args.n_tiles != 1) {
-      snprintf(err, errlen, "stem wgrad: needs bn 64, a 16x8x1 pixel box and Cout <= 64");
+  if (args.stem) {  // igemm_wgrad_halo_kernel: several taps per pass over the pixels
+    const long long b_box = static_cast<long long>(args.box_w) * args.halo_rows * 128;
+    const long long stage = 128 * 128 + args.halo_boxes * b_box;
+    const bool geo_ok = (args.box_w == 16 && args.box_h == 8) || (args.box_w == 8 && args.box_h == 16);
+    if (bn != 64 || !geo_ok || args.box_n != 1 || args.m_valid > 64 || args.m_tiles != 1 ||
+        args.n_tiles != 1 || args.halo_nacc < 1 || args.halo_nacc > 8 || args.halo_boxes < 1 ||
+        args.halo_boxes > 3 || stage % 1024 != 0 || stage * 2 > 216 * 1024 ||
+        args.halo_rowbytes % 1024 != 0) {
+      snprintf(err, errlen, "halo wgrad: bad geometry (bn 64, 16x8 or 8x16 box, Cout <= 64, <= 8 taps)");
       delete p;
       return nullptr;
     }
+    p->wa.halo_stages = static_cast<int>((216 * 1024) / stage > 3 ? 3 : (216 * 1024) / stage);
     p->total_work = args.k_splits;
   }
   p->grid = p->total_work < num_sms ? p->total_work : num_sms;

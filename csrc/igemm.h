@@ -69,7 +69,13 @@ struct WgradArgs {
   int m_valid, n_valid;           // Cout, Cin
   int ldw;                        // dW row pitch in elements (= taps * Cin)
   float* dw;                      // fp32, accumulated with red.global.add
-  int stem;                       // 7x7/2 stem: all seven filter rows from one halo box
+  int stem;                       // halo mode (igemm_wgrad_halo_kernel): 1 = 7x7/2 stem, 2 = 3x3
+  // halo mode geometry (filled by the plan builder, see igemm_wgrad.cu)
+  int halo_boxes, halo_rows;      // B boxes per stage (w shifts) and input rows per box
+  int halo_hmul, halo_h0;         // B row origin = tile row * box_h * hmul + h0
+  int halo_jmul, halo_rowbytes;   // K slice j of accumulator t reads B at (j*jmul + acc_row[t]) * rowbytes
+  int halo_nacc, halo_stages;
+  int acc_box[kMaxTaps], acc_row[kMaxTaps], box_dw[3];
   int wide;                       // 256 x 256 tile per CTA (igemm_wgrad_wide_kernel), boxes <= 64 px
 };
 

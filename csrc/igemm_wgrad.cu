@@ -135,11 +135,12 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           tc_fence_after();
           const uint32_t a_base = smem_u32(smem + stage * Cfg::kStage);
           const uint32_t b_base = a_base + Cfg::kAStage;
-          for (int k = 0; k < mmas; ++k) {
-            const uint64_t adesc = umma_desc_sw128(a_base + k * 2048, box_bytes, 1024);
-            const uint64_t bdesc = umma_desc_sw128(b_base + k * 2048, box_bytes, 1024);
-            umma_bf16(d_tmem, adesc, bdesc, idesc, (b > b0 || k > 0) ? 1u : 0u);
-          }
+          // one thread issues every MMA: keep its per-MMA work to two 64-bit adds (the start
+          // address is the low field of the descriptor; 2048 B = 128 units of 16 B)
+          const uint64_t ad0 = umma_desc_sw128(a_base, box_bytes, 1024);
+          const uint64_t bd0 = umma_desc_sw128(b_base, box_bytes, 1024);
+          for (int k = 0; k < mmas; ++k)
+            umma_bf16(d_tmem, ad0 + k * 128, bd0 + k * 128, idesc, (b > b0 || k > 0) ? 1u : 0u);
           umma_commit(&empty[stage]);
           if (++stage == Cfg::kStages) {
             stage = 0;
@@ -195,35 +196,39 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 
-// ------------------------------------------------------------- stem wgrad
-// 7x7 / stride-2 stem on the window-row layout (ops/igemm.py): dW[m, r, 0..63] for all seven
-// filter rows r from ONE pass over the pixels.  Per stage of 16 x 8 output pixels:
-//   A = dY box  [128 pixels][64 channels]              16 KB  (MN-major, M = Cout = 64)
-//   B = X  box  [21 input rows x 16 window columns][64] 42 KB  (MN-major, N = 64)
-// Output row j (16 pixels = one K=16 slice = 2048 B) of filter row r multiplies box row 2j + r,
-// so the seven filter rows differ only in the B descriptor's start address; they accumulate
-// into seven 64-column TMEM accumulators (448 of 512 columns).  Compared with one pass per
-// filter row (the generic kernel) the L2 -> SM traffic drops 3.9x, which is what bounded it.
+// ------------------------------------------------------------- halo wgrad
+// Several filter taps from ONE pass over the pixels, for layers whose Cout x Cin tile is so small
+// (64 x 64) that the generic kernel - one pass per tap - is bound by re-reading the same pixels
+// through the L2 -> SM fabric.  Per stage of 128 output pixels:
+//   A = dY box [128 pixels][64 channels], 16 KB (MN-major, M = Cout = 64)
+//   B = 1 or 3 X halo boxes (the box's w origin shifted by box_dw[i]) that also cover the input
+//       rows above / below; accumulator t multiplies K slice j (16 pixels = 2048 B of A) with the
+//       B rows at (j * jmul + acc_row[t]) * rowbytes of box acc_box[t] - a filter tap only moves
+//       the descriptor's start address, by a multiple of 1024 B (SWIZZLE_128B atoms stay aligned).
+// Each accumulator is 64 TMEM columns (up to 8 of them = 512 columns, single-buffered).
+//   stem 7x7/2 (window-row layout, ops/igemm.py): 16 x 8 pixels, one 16 x 21 box, 7 accumulators
+//     (filter rows), K slice j = output row j, B row 2j + r;          3.9x fewer bytes than 7 passes
+//   3x3/1 64->64: 8 x 16 pixels, three 8 x 18 boxes (dw = -1, 0, +1), 8 accumulators (all taps but
+//     the centre, which the generic kernel adds), K slice j = output rows 2j, 2j+1 (2 x 1024 B),
+//     B row 2j + dh + 1;                                              4x fewer bytes than 9 passes
 // The MMA is M = 128 wide; rows 64..127 of every accumulator are scratch (their A "half" is
 // whatever follows the dY box in shared memory) and are never read.
-constexpr int kStemBW = 16, kStemBH = 8, kStemXRows = 2 * kStemBH + 5;
-constexpr int kStemA = kStemBW * kStemBH * 128;      // 16384
-constexpr int kStemB = kStemBW * kStemXRows * 128;   // 43008
-constexpr int kStemStage = kStemA + kStemB;          // 59392 (multiple of 1024)
-constexpr int kStemStages = 3;
-constexpr int kStemSmem = kStemStages * kStemStage + 256 + 1024;
+constexpr int kHaloA = 128 * 128;                    // dY box: 128 pixels x 64 channels x 2 B
+constexpr int kHaloMaxStages = 3;
+constexpr int kHaloSmemData = 216 * 1024;            // stem 3 x 58 KB, 3x3 3 x 70 KB
+constexpr int kHaloSmem = kHaloSmemData + 256 + 1024;
 
 __global__ void __launch_bounds__(kThreads, 1)
-igemm_wgrad_stem_kernel(const __grid_constant__ CUtensorMap tmA,
+igemm_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmA,
                         const __grid_constant__ CUtensorMap tmB, const WgradArgs a,
                         const int total_work) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStemStages * kStemStage);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kHaloSmemData);
   uint64_t* full = bars;
-  uint64_t* empty = bars + kStemStages;
-  uint64_t* tfull = bars + 2 * kStemStages;
+  uint64_t* empty = bars + kHaloMaxStages;
+  uint64_t* tfull = bars + 2 * kHaloMaxStages;
   uint64_t* tempty = tfull + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 1);
 
@@ -232,7 +237,7 @@ igemm_wgrad_stem_kernel(const __grid_constant__ CUtensorMap tmA,
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int i = 0; i < kStemStages; ++i) {
+    for (int i = 0; i < kHaloMaxStages; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
@@ -251,6 +256,9 @@ igemm_wgrad_stem_kernel(const __grid_constant__ CUtensorMap tmA,
 
   const int total_boxes = a.tiles_w * a.tiles_h * a.tiles_n;
   const int per_split = (total_boxes + a.k_splits - 1) / a.k_splits;
+  const uint32_t b_box = static_cast<uint32_t>(a.box_w) * a.halo_rows * 128u;   // one halo box
+  const uint32_t stage_bytes = kHaloA + a.halo_boxes * b_box;                   // multiple of 1024
+  const int nstages = a.halo_stages;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -263,12 +271,13 @@ igemm_wgrad_stem_kernel(const __grid_constant__ CUtensorMap tmA,
           const int th = (b / a.tiles_w) % a.tiles_h;
           const int tn = b / (a.tiles_w * a.tiles_h);
           mbar_wait(&empty[stage], phase ^ 1);
-          uint8_t* sA = smem + stage * kStemStage;
-          mbar_expect_tx(&full[stage], kStemStage);
-          tma_load_4d(sA, &tmA, &full[stage], 0, tw * kStemBW, th * kStemBH, tn);
-          tma_load_4d(sA + kStemA, &tmB, &full[stage], 0, tw * kStemBW + a.tap_dw[0],
-                      th * kStemBH * 2 + a.tap_dh[0], tn);
-          if (++stage == kStemStages) {
+          uint8_t* sA = smem + stage * stage_bytes;
+          mbar_expect_tx(&full[stage], stage_bytes);
+          tma_load_4d(sA, &tmA, &full[stage], 0, tw * a.box_w, th * a.box_h, tn);
+          for (int i = 0; i < a.halo_boxes; ++i)
+            tma_load_4d(sA + kHaloA + i * b_box, &tmB, &full[stage], 0, tw * a.box_w + a.box_dw[i],
+                        th * a.box_h * a.halo_hmul + a.halo_h0, tn);
+          if (++stage == nstages) {
             stage = 0;
             phase ^= 1;
           }
@@ -280,6 +289,10 @@ igemm_wgrad_stem_kernel(const __grid_constant__ CUtensorMap tmA,
       constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, 64, true, true);
       int stage = 0;
       uint32_t phase = 0, acc_phase = 0;
+      uint32_t acc_off[kMaxTaps];   // descriptor offset (16-byte units) of each accumulator's B rows
+      for (int t = 0; t < kMaxTaps; ++t)
+        acc_off[t] = (a.acc_box[t] * b_box + a.acc_row[t] * a.halo_rowbytes) >> 4;
+      const uint32_t jstep = (a.halo_jmul * a.halo_rowbytes) >> 4;
       for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
         const int b0 = work * per_split, b1 = min(b0 + per_split, total_boxes);
         mbar_wait(tempty, acc_phase ^ 1);
@@ -287,19 +300,22 @@ igemm_wgrad_stem_kernel(const __grid_constant__ CUtensorMap tmA,
         for (int b = b0; b < b1; ++b) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(smem + stage * kStemStage);
-          const uint32_t b_base = a_base + kStemA;
-          for (int r = 0; r < 7; ++r) {
+          const uint32_t a_base = smem_u32(smem + stage * stage_bytes);
+          const uint32_t b_base = a_base + kHaloA;
+          // A: second 64-row half = kHaloA bytes further on (scratch rows, see above).  One thread
+          // issues all 56-64 MMAs of a stage: descriptors advance by plain 64-bit adds.
+          const uint64_t ad0 = umma_desc_sw128(a_base, kHaloA, 1024);
+          const uint64_t bd0 = umma_desc_sw128(b_base, 2048, 1024);
+          const uint32_t first = (b > b0) ? 1u : 0u;
+          for (int t = 0; t < a.halo_nacc; ++t) {
+            const uint64_t bt = bd0 + acc_off[t];
+            const uint32_t d = tmem_base + t * 64;
+            umma_bf16(d, ad0, bt, idesc, first);
 #pragma unroll
-            for (int j = 0; j < kStemBH; ++j) {
-              // A: second 64-row half = kStemA bytes further on (scratch rows, see above)
-              const uint64_t adesc = umma_desc_sw128(a_base + j * 2048, kStemA, 1024);
-              const uint64_t bdesc = umma_desc_sw128(b_base + (2 * j + r) * 2048, 2048, 1024);
-              umma_bf16(tmem_base + r * 64, adesc, bdesc, idesc, (b > b0 || j > 0) ? 1u : 0u);
-            }
+            for (int j = 1; j < 8; ++j) umma_bf16(d, ad0 + j * 128, bt + j * jstep, idesc, 1u);
           }
           umma_commit(&empty[stage]);
-          if (++stage == kStemStages) {
+          if (++stage == nstages) {
             stage = 0;
             phase ^= 1;
           }
@@ -319,12 +335,12 @@ igemm_wgrad_stem_kernel(const __grid_constant__ CUtensorMap tmA,
       tc_fence_after();
       if (q < 2) {
 #pragma unroll 1
-        for (int c = 0; c < 14; ++c) {  // 7 filter rows x two 32-column chunks
+        for (int c = 0; c < 2 * a.halo_nacc; ++c) {  // accumulators x two 32-column chunks
           uint32_t v[32];
           tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, v);
           tmem_ld_wait();
           if (valid) {
-            float* o = a.dw + static_cast<long long>(m) * a.ldw + c * 32;
+            float* o = a.dw + static_cast<long long>(m) * a.ldw + a.tap_out[c >> 1] + (c & 1) * 32;
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
               red_add_f32x4(o + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]),
@@ -455,14 +471,13 @@ igemm_wgrad_wide_kernel(const __grid_constant__ CUtensorMap tmA,
           tc_fence_after();
           const uint32_t a_base = smem_u32(smem + stage * kWideStage);
           const uint32_t b_base = a_base + 4 * kWideBox;
+          const uint64_t ad0 = umma_desc_sw128(a_base, box_bytes, 1024);
+          const uint64_t ad1 = umma_desc_sw128(a_base + 2 * box_bytes, box_bytes, 1024);
+          const uint64_t bd0 = umma_desc_sw128(b_base, box_bytes, 1024);
           for (int k = 0; k < mmas; ++k) {
-            const uint64_t bdesc = umma_desc_sw128(b_base + k * 2048, box_bytes, 1024);
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt) {
-              const uint64_t adesc =
-                  umma_desc_sw128(a_base + mt * 2 * box_bytes + k * 2048, box_bytes, 1024);
-              umma_bf16(tmem_base + mt * 256, adesc, bdesc, idesc, (b > b0 || k > 0) ? 1u : 0u);
-            }
+            const uint32_t accf = (b > b0 || k > 0) ? 1u : 0u;
+            umma_bf16(tmem_base, ad0 + k * 128, bd0 + k * 128, idesc, accf);
+            umma_bf16(tmem_base + 256, ad1 + k * 128, bd0 + k * 128, idesc, accf);
           }
           umma_commit(&empty[stage]);
           if (++stage == kWideStages) {
@@ -536,12 +551,12 @@ cudaError_t launch_wgrad_wide(const IGemmPlan* p, cudaStream_t s) {
 cudaError_t launch_wgrad_stem(const IGemmPlan* p, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_wgrad_stem_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kStemSmem);
+    cudaError_t e = cudaFuncSetAttribute(igemm_wgrad_halo_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmem);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  igemm_wgrad_stem_kernel<<<p->grid, kThreads, kStemSmem, s>>>(p->tmA, p->tmB, p->wa,
+  igemm_wgrad_halo_kernel<<<p->grid, kThreads, kHaloSmem, s>>>(p->tmA, p->tmB, p->wa,
                                                               p->total_work);
   return cudaGetLastError();
 }

@@ -24,6 +24,8 @@ _WGRAD_WIDE = os.environ.get("TFOS_WGRAD_WIDE", "1") == "1"
 _WGRAD_WIDE_MIN_PIXELS = int(os.environ.get("TFOS_WGRAD_WIDE_MIN_PIXELS", "32768"))
 _WGRAD_WORK = int(os.environ.get("TFOS_WGRAD_WORK", "0"))  # 0: per-layer heuristic
 _STEM_HALO = os.environ.get("TFOS_STEM_HALO", "1") == "1"
+_WGRAD_HALO = os.environ.get("TFOS_WGRAD_HALO", "1") == "1"
+_WGRAD_HALO_MIN_PIXELS = int(os.environ.get("TFOS_WGRAD_HALO_MIN_PIXELS", "16384"))
 _STEM_SPLITS = int(os.environ.get("TFOS_STEM_SPLITS", "148"))
 
 
@@ -312,6 +314,31 @@ def _wgrad_plan(dy, dy_whn, Cout, x, x_whn, Cin, dw, ldw, taps, mul, es, box=Non
       " wide" if wide else "", Cin, Cout, len(taps), k_splits))
 
 
+def _wgrad3x3_halo_plan(dy, x, dw):
+  """3x3 / stride 1 / pad 1 with Cin = 64, Cout <= 64: eight taps in one pass over the pixels
+  (csrc/igemm_wgrad.cu igemm_wgrad_halo_kernel), the centre tap by the generic kernel."""
+  N, OH, OW, Cout = dy.shape
+  _, H, W, Cin = x.shape
+  ta = _tmap4(dy, (OW, OH, N), Cout, (8, 16, 1))
+  tb = _tmap4(x, (W, H, N), Cin, (8, 16 + 2, 1))
+  taps = [(dh, dw_) for dh in (-1, 0, 1) for dw_ in (-1, 0, 1) if (dh, dw_) != (0, 0)]
+  tw, th = -(-OW // 8), -(-OH // 16)
+  g = {
+      "tiles_w": tw, "tiles_h": th, "tiles_n": N, "box_w": 8, "box_h": 16, "box_n": 1,
+      "num_taps": 1, "stem": 2,
+      "halo_boxes": 3, "box_dw": [-1, 0, 1], "halo_rows": 16 + 2, "halo_hmul": 1, "halo_h0": -1,
+      "halo_jmul": 2, "halo_rowbytes": 1024, "halo_nacc": 8,
+      "acc_box": [d + 1 for (_, d) in taps], "acc_row": [dh + 1 for (dh, _) in taps],
+      "tap_out": [((dh + 1) * 3 + (d + 1)) * Cin for (dh, d) in taps],
+      "m_tiles": 1, "n_tiles": 1, "k_splits": max(1, min(_STEM_SPLITS, tw * th * N)),
+      "m_valid": Cout, "n_valid": 64, "ldw": 9 * Cin, "dw": dw.data_ptr(),
+  }
+  halo = _C().igemm_plan_wgrad(ta, tb, g, 64)
+  centre = _wgrad_plan(dy, (OW, OH, N), Cout, x, (W, H, N), Cin, dw, 9 * Cin, [(0, 0, 4 * Cin)], 1, 1)
+  handles, centre.handles = [halo] + centre.handles, []   # this plan owns (and frees) them all
+  return Plan(handles, (dy, x, dw), "wgrad 3x3 halo {}->{}".format(Cin, Cout))
+
+
 def conv_wgrad(dy, x, dw, stride=1, pad=0):
   """dw[Cout,R,S,Cin] (fp32, +=) = sum_pixels dy[.,Cout]^T x_shifted[.,Cin]."""
   N, OH, OW, Cout = dy.shape
@@ -319,6 +346,9 @@ def conv_wgrad(dy, x, dw, stride=1, pad=0):
   _, R, S, _ = dw.shape
   if R == 1 and S == 1 and stride == 1 and pad == 0:
     return gemm_wgrad(dy.view(-1, Cout), x.view(-1, Cin), dw.view(Cout, Cin))
+  if (_WGRAD_HALO and R == 3 and S == 3 and stride == 1 and pad == 1 and Cin == 64 and Cout <= 64
+      and Cout % 8 == 0 and N * OH * OW >= _WGRAD_HALO_MIN_PIXELS):
+    return _wgrad3x3_halo_plan(dy, x, dw)
   taps = [(s - pad, r - pad, (r * S + s) * Cin) for r in range(R) for s in range(S)]
   return _wgrad_plan(dy, (OW, OH, N), Cout, x, (W, H, N), Cin, dw, R * S * Cin, taps, stride,
                      stride)
@@ -415,7 +445,10 @@ def stem_wgrad(dy, xp, dw):
     tw, th = -(-OW // 16), -(-OH // 8)
     g = {
         "tiles_w": tw, "tiles_h": th, "tiles_n": N, "box_w": 16, "box_h": 8, "box_n": 1,
-        "num_taps": 1, "tap_dw": [0], "tap_dh": [-STEM_PAD], "stem": 1,
+        "num_taps": 1, "stem": 1,
+        "halo_boxes": 1, "box_dw": [0], "halo_rows": 2 * 8 + 5, "halo_hmul": 2,
+        "halo_h0": -STEM_PAD, "halo_jmul": 2, "halo_rowbytes": 2048, "halo_nacc": 7,
+        "acc_box": [0] * 7, "acc_row": list(range(7)), "tap_out": [r * 64 for r in range(7)],
         "m_tiles": 1, "n_tiles": 1, "k_splits": max(1, min(_STEM_SPLITS, tw * th * N)),
         "m_valid": Cout, "n_valid": 64, "ldw": 7 * 64, "dw": dw.data_ptr(),
     }
