@@ -361,6 +361,7 @@ def run(fn, tf_args, cluster_meta, tensorboard, log_dir, queues, background):
     def wrapper_fn(args, context):
       if isinstance(args, list):
         sys.argv = args
+      _start_heartbeat(context.mgr)
       fn(args, context)
 
     def wrapper_fn_background(args, context):
@@ -470,7 +471,42 @@ def _feed(queue, ring, iterator):
   return count
 
 
-def _await_consumption(queue, equeue, feed_timeout, what, low_water=0):
+HEARTBEAT_KEY = "heartbeat"
+
+
+def _start_heartbeat(mgr):
+  """Daemon thread of the process that runs the user function: stamps the manager's key/value
+  store every TFOS_HEARTBEAT_SECS (default 2 s).  Feeder tasks use the stamp to tell "the node is
+  busy" from "the node process is gone" without waiting for feed_timeout (10 min): a node killed
+  by the OOM killer or a CUDA trap that took the process down never reaches its error queue."""
+  period = float(os.environ.get("TFOS_HEARTBEAT_SECS", "2"))
+  if period <= 0:
+    return None
+
+  def beat():
+    while True:
+      try:
+        mgr.set(HEARTBEAT_KEY, time.time())
+      except Exception:
+        return   # manager gone: the executor is shutting down
+      time.sleep(period)
+
+  t = threading.Thread(target=beat, name="tfos-heartbeat", daemon=True)
+  t.start()
+  return t
+
+
+def _heartbeat_age(mgr):
+  """Seconds since the node's last heartbeat, or None if it never sent one."""
+  try:
+    v = mgr.get(HEARTBEAT_KEY)
+    v = v._getvalue() if hasattr(v, "_getvalue") else v
+    return None if v is None else max(0.0, time.time() - float(v))
+  except Exception:
+    return None
+
+
+def _await_consumption(queue, equeue, feed_timeout, what, low_water=0, mgr=None):
   """Wait until the consumer has task_done()'d everything; surface worker errors and hangs.
 
   ``low_water`` > 0 (training feed): return as soon as at most that many posted chunks are
@@ -498,6 +534,13 @@ def _await_consumption(queue, equeue, feed_timeout, what, low_water=0):
     waited += step
     if waited > feed_timeout:
       raise Exception("Timeout while feeding partition ({})".format(what))
+    if mgr is not None and step >= 1.0:
+      age = _heartbeat_age(mgr)
+      limit = float(os.environ.get("TFOS_HEARTBEAT_TIMEOUT", "60"))
+      if age is not None and limit > 0 and age > limit:
+        raise Exception("node process stopped responding: last heartbeat {:.0f} s ago while "
+                        "feeding ({}); look for an OOM kill or a CUDA error in the executor log"
+                        .format(age, what))
 
 
 def train(cluster_info, cluster_meta, feed_timeout=600, qname="input"):
@@ -518,7 +561,7 @@ def train(cluster_info, cluster_meta, feed_timeout=600, qname="input"):
       logger.info("feeding partition into the %s queue", qname)
       count = _feed(queue, _ring_of(mgr), iter)
       _await_consumption(queue, equeue, feed_timeout, "train",
-                         int(os.environ.get("TFOS_FEED_LOW_WATER", "1")))
+                         int(os.environ.get("TFOS_FEED_LOW_WATER", "1")), mgr)
       logger.info("processed %d items in partition", count)
     if _state(mgr) == "terminating":
       # the consumer asked to stop: let the driver (streaming shutdown) know
@@ -549,7 +592,7 @@ def inference(cluster_info, feed_timeout=600, qname="input"):
     queue_in.put(marker.EndPartition())
     if count == 0:
       return []
-    _await_consumption(queue_in, equeue, feed_timeout, "inference")
+    _await_consumption(queue_in, equeue, feed_timeout, "inference", 0, mgr)
     logger.info("processed %d items in partition", count)
     results = []
     queue_out = mgr.get_queue("output")

@@ -17,6 +17,7 @@ with open(_FAKE_TB, "w") as _f:
   _f.write("#!/bin/sh\necho \"$@\" > {}/args.txt\nexec sleep 600\n".format(_FAKE_DIR))
 os.chmod(_FAKE_TB, os.stat(_FAKE_TB).st_mode | stat.S_IEXEC)
 os.environ["PATH"] = _FAKE_DIR + os.pathsep + os.environ.get("PATH", "")
+os.environ["TFOS_HEARTBEAT_TIMEOUT"] = "3"   # likewise inherited by the executors at fork time
 
 
 def _alive(pid):
@@ -146,6 +147,26 @@ def test_cluster_run_gives_up_when_nodes_are_missing(sc):
 
   with pytest.raises(Exception):
     TFCluster.run(sc, fn, {}, 2, 0, reservation_timeout=0)
+
+
+def test_silent_node_death_is_detected_by_heartbeat(sc):
+  """A node process that vanishes without raising (OOM kill, CUDA trap taking the process down)
+  never writes to its error queue; the feeder must notice the missing heartbeats long before
+  feed_timeout."""
+  def fn(args, ctx):
+    feed = ctx.get_data_feed(train_mode=True)
+    feed.next_batch(4)
+    os._exit(17)          # no exception, no error-queue entry, heartbeat thread dies with us
+
+  cluster = TFCluster.run(sc, fn, {}, 2, 0, input_mode=TFCluster.InputMode.SPARK)
+  t0 = time.time()
+  with pytest.raises(Exception, match="heartbeat"):
+    cluster.train(sc.parallelize(range(1000), 2), feed_timeout=120)
+  assert time.time() - t0 < 60
+  try:
+    cluster.shutdown(grace_secs=0, timeout=30)
+  except BaseException:
+    pass
 
 
 def test_shutdown_watchdog_fires(sc):
