@@ -114,6 +114,39 @@ def reference_arm(args):
   return 0
 
 
+class Watchdog(object):
+  """A benchmark must never hang its caller.  If no result was printed after ``seconds``
+  (TFOS_BENCH_WATCHDOG_S, default 480; a 1-GPU run takes about a minute), dump every thread's
+  stack to stderr and leave: with the kernel-timed result (and a note) if that part had finished -
+  e.g. when only the end-to-end section stalled - else with exit code 3."""
+
+  def __init__(self, seconds, rank):
+    import threading
+    self.partial, self.rank, self.seconds = None, rank, seconds
+    self.timer = threading.Timer(seconds, self._fire)
+    self.timer.daemon = True
+    if seconds > 0:
+      self.timer.start()
+
+  def _fire(self):
+    import faulthandler
+    sys.stderr.write("bench.py watchdog: no result after {} s; thread stacks follow\n".format(
+        self.seconds))
+    faulthandler.dump_traceback(file=sys.stderr, all_threads=True)
+    sys.stderr.flush()
+    if self.partial is not None:   # every rank leaves cleanly; rank 0 reports
+      if self.rank == 0:
+        out = dict(self.partial, watchdog="a later section did not finish within {} s".format(
+            self.seconds))
+        print(json.dumps(out))
+        sys.stdout.flush()
+      os._exit(0)
+    os._exit(3)
+
+  def cancel(self):
+    self.timer.cancel()
+
+
 def main():
   args = parse_args()
   if args.impl == "reference":
@@ -121,6 +154,7 @@ def main():
 
   import torch
   rank = int(os.environ.get("RANK", "0"))
+  watchdog = Watchdog(float(os.environ.get("TFOS_BENCH_WATCHDOG_S", "480")), rank)
   world = int(os.environ.get("WORLD_SIZE", "1"))
   local_rank = int(os.environ.get("LOCAL_RANK", "0"))
   if world != args.gpus and world > 1:
@@ -195,6 +229,14 @@ def main():
   ms_max = float(t)
   ms_per_step = ms_max / args.steps
   value = B * world * args.steps / (ms_max / 1e3)
+  watchdog.partial = {
+      "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+      "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
+      "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "impl": "ours",
+      "data": "synthetic (uint8 224x224x3 ImageNet-shaped, random-init weights)",
+      "config": {"model": "resnet50_v1.5", "global_batch": B * world, "per_gpu_batch": B,
+                 "image": args.image, "parallelism": "dp{}".format(world)},
+      "clocks": clocks, "gpu_launches": launches_per_step * args.steps}
 
   # ------------------------------------------------------------------------ e2e
   e2e = None
@@ -279,6 +321,8 @@ def main():
     if exposed is not None:
       out["exposed_allreduce_ms_per_step"] = exposed
     print(json.dumps(out))
+    sys.stdout.flush()
+  watchdog.cancel()
   if dist is not None:
     dist.barrier()
     dist.destroy_process_group()
