@@ -116,7 +116,7 @@ def reference_arm(args):
 
 class Watchdog(object):
   """A benchmark must never hang its caller.  If no result was printed after ``seconds``
-  (TFOS_BENCH_WATCHDOG_S, default 480; a 1-GPU run takes about a minute), dump every thread's
+  (TFOS_BENCH_WATCHDOG_S, default 300; a 1-GPU run takes about a minute), dump every thread's
   stack to stderr and leave: with the kernel-timed result (and a note) if that part had finished -
   e.g. when only the end-to-end section stalled - else with exit code 3."""
 
@@ -154,7 +154,7 @@ def main():
 
   import torch
   rank = int(os.environ.get("RANK", "0"))
-  watchdog = Watchdog(float(os.environ.get("TFOS_BENCH_WATCHDOG_S", "480")), rank)
+  watchdog = Watchdog(float(os.environ.get("TFOS_BENCH_WATCHDOG_S", "300")), rank)
   world = int(os.environ.get("WORLD_SIZE", "1"))
   local_rank = int(os.environ.get("LOCAL_RANK", "0"))
   if world != args.gpus and world > 1:
