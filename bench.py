@@ -329,5 +329,42 @@ def main():
   return 0
 
 
+def supervised_main():
+  """Single-process runs (the driver's N = 1 arm, `python bench.py ...`) are executed in a child
+  process under a timeout and retried once: a stalled box must cost one retry, not the headline
+  number.  torchrun ranks (WORLD_SIZE set) and the reference arm run directly."""
+  args = parse_args()
+  if (args.impl != "ours" or args.profile_step or os.environ.get("TFOS_BENCH_CHILD") == "1"
+      or int(os.environ.get("WORLD_SIZE", "1")) > 1 or "RANK" in os.environ
+      or os.environ.get("TFOS_BENCH_SUPERVISE", "1") == "0"):
+    return main()
+  try:   # the parent maps the native extension too: it is this repo's code that is being timed
+    from tensorflowonspark_b200 import _build
+    _build.load(required=True)
+  except Exception as e:
+    sys.stderr.write("bench.py: extension not loadable in the supervisor: {}\n".format(e))
+  limit = float(os.environ.get("TFOS_BENCH_WATCHDOG_S", "300")) + 60
+  env = dict(os.environ, TFOS_BENCH_CHILD="1")
+  last = None
+  for attempt in (1, 2):
+    try:
+      p = subprocess.run([sys.executable, os.path.abspath(__file__)] + sys.argv[1:], env=env,
+                         stdout=subprocess.PIPE, text=True, timeout=limit)
+      lines = [l for l in p.stdout.splitlines() if l.startswith("{") and '"metric"' in l]
+      if p.returncode == 0 and lines:
+        rec = json.loads(lines[-1])
+        if attempt > 1:
+          rec["attempt"] = attempt
+        print(json.dumps(rec))
+        return 0
+      last = "exit code {} and {} result lines".format(p.returncode, len(lines))
+      sys.stderr.write(p.stdout[-2000:])
+    except subprocess.TimeoutExpired:
+      last = "no result within {:.0f} s".format(limit)
+    sys.stderr.write("bench.py: attempt {} failed ({}){}\n".format(
+        attempt, last, "; retrying" if attempt == 1 else ""))
+  return 3
+
+
 if __name__ == "__main__":
-  sys.exit(main())
+  sys.exit(supervised_main())
