@@ -1,0 +1,71 @@
+"""bench.py contract pieces that can be checked without a GPU: the reference arm's
+"unavailable" line, the watchdog (a stalled section must not hang the caller and must not lose
+the kernel-timed number), the supervisor's retry."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BENCH = os.path.join(ROOT, "bench.py")
+
+
+def test_reference_arm_reports_unavailable_and_exits_zero():
+  p = subprocess.run([sys.executable, BENCH, "--impl", "reference", "--gpus", "1", "--steps", "2",
+                      "--warmup", "3"], capture_output=True, text=True, timeout=120)
+  assert p.returncode == 0
+  rec = json.loads(p.stdout.strip().splitlines()[-1])
+  assert rec["impl"] == "reference" and isinstance(rec["unavailable"], str) and rec["unavailable"]
+
+
+def _load_bench():
+  import importlib.util
+  spec = importlib.util.spec_from_file_location("bench_under_test", BENCH)
+  mod = importlib.util.module_from_spec(spec)
+  argv, sys.argv = sys.argv, ["bench.py"]
+  try:
+    spec.loader.exec_module(mod)
+  finally:
+    sys.argv = argv
+  return mod
+
+
+def test_watchdog_prints_partial_result_and_exits_cleanly():
+  code = (
+      "import sys, time, importlib.util\n"
+      "sys.argv = ['bench.py']\n"
+      "spec = importlib.util.spec_from_file_location('b', {!r})\n"
+      "b = importlib.util.module_from_spec(spec); spec.loader.exec_module(b)\n"
+      "w = b.Watchdog(0.3, 0)\n"
+      "w.partial = {{'metric': 'm', 'value': 1.5}}\n"
+      "time.sleep(20)\n"
+      "print('NOT REACHED')\n").format(BENCH)
+  p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=60)
+  assert p.returncode == 0 and "NOT REACHED" not in p.stdout
+  rec = json.loads(p.stdout.strip().splitlines()[-1])
+  assert rec["value"] == 1.5 and "watchdog" in rec
+  assert "thread stacks follow" in p.stderr
+
+
+def test_watchdog_without_result_exits_nonzero():
+  code = (
+      "import sys, time, importlib.util\n"
+      "sys.argv = ['bench.py']\n"
+      "spec = importlib.util.spec_from_file_location('b', {!r})\n"
+      "b = importlib.util.module_from_spec(spec); spec.loader.exec_module(b)\n"
+      "w = b.Watchdog(0.3, 0)\n"
+      "time.sleep(20)\n").format(BENCH)
+  p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=60)
+  assert p.returncode == 3 and p.stdout.strip() == ""
+
+
+def test_supervisor_retries_once_then_gives_up_without_a_gpu():
+  import torch
+  if torch.cuda.is_available():
+    import pytest
+    pytest.skip("meaningful only where the benchmark itself cannot run")
+  p = subprocess.run([sys.executable, BENCH, "--steps", "2", "--warmup", "3"], capture_output=True,
+                     text=True, timeout=300)
+  assert p.returncode == 3
+  assert "attempt 1 failed" in p.stderr and "attempt 2 failed" in p.stderr
+  assert not [l for l in p.stdout.splitlines() if l.startswith("{")]
