@@ -64,8 +64,11 @@ def test_supervisor_retries_once_then_gives_up_without_a_gpu():
   if torch.cuda.is_available():
     import pytest
     pytest.skip("meaningful only where the benchmark itself cannot run")
+  # (earlier tests of this session export RANK / WORLD_SIZE into os.environ: start clean)
+  env = {k: v for k, v in os.environ.items()
+         if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "TFOS_BENCH_CHILD", "TFOS_BENCH_SUPERVISE")}
   p = subprocess.run([sys.executable, BENCH, "--steps", "2", "--warmup", "3"], capture_output=True,
-                     text=True, timeout=300)
+                     text=True, timeout=300, env=env)
   assert p.returncode == 3
   assert "attempt 1 failed" in p.stderr and "attempt 2 failed" in p.stderr
   assert not [l for l in p.stdout.splitlines() if l.startswith("{")]
