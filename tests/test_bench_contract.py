@@ -72,3 +72,33 @@ def test_supervisor_retries_once_then_gives_up_without_a_gpu():
   assert p.returncode == 3
   assert "attempt 1 failed" in p.stderr and "attempt 2 failed" in p.stderr
   assert not [l for l in p.stdout.splitlines() if l.startswith("{")]
+
+
+def _supervise(child_code, watchdog_s="1"):
+  env = {k: v for k, v in os.environ.items()
+         if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "TFOS_BENCH_CHILD", "TFOS_BENCH_SUPERVISE")}
+  env["TFOS_BENCH_CHILD_CMD"] = json.dumps([sys.executable, "-c", child_code])
+  env["TFOS_BENCH_WATCHDOG_S"] = watchdog_s
+  return subprocess.run([sys.executable, BENCH, "--steps", "2", "--warmup", "3"],
+                        capture_output=True, text=True, timeout=400, env=env)
+
+
+def test_supervisor_passes_the_childs_result_line_through():
+  p = _supervise("print('NCCL version noise'); print('{\"metric\": \"m\", \"value\": 2.5, \"n_gpus\": 1}')")
+  assert p.returncode == 0
+  lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
+  assert len(lines) == 1 and json.loads(lines[0]) == {"metric": "m", "value": 2.5, "n_gpus": 1}
+
+
+def test_supervisor_retries_a_stalled_child(tmp_path):
+  marker = str(tmp_path / "first_attempt_done")
+  code = ("import os, sys, time\n"
+          "m = {!r}\n"
+          "if not os.path.exists(m):\n"
+          "  open(m, 'w').close(); time.sleep(600)\n"
+          "print('{{\"metric\": \"m\", \"value\": 7}}')\n").format(marker)
+  p = _supervise(code, watchdog_s="-55")   # limit = watchdog + 60 = 5 s
+  assert p.returncode == 0, p.stderr[-500:]
+  rec = json.loads([l for l in p.stdout.splitlines() if l.startswith("{")][-1])
+  assert rec["value"] == 7 and rec["attempt"] == 2
+  assert "attempt 1 failed (no result within" in p.stderr
