@@ -70,7 +70,11 @@ if __name__ == "__main__":
   args = parser.parse_args()
   sc = SparkContext(conf=SparkConf().setAppName("mnist_estimator").set(
       "spark.executor.instances", str(args.cluster_size)))
-  rows = sc.textFile(args.images_labels).map(lambda line: [int(x) for x in line.split(",")])
+  def parse(line):
+    import numpy as np
+    return np.fromstring(line, dtype=np.int64, sep=",")   # one C-level parse per CSV line
+
+  rows = sc.textFile(args.images_labels).map(parse)
   cluster = TFCluster.run(sc, main_fun, args, args.cluster_size, num_ps=0,
                           tensorboard=args.tensorboard, input_mode=TFCluster.InputMode.SPARK,
                           log_dir=args.model_dir, master_node="chief")
