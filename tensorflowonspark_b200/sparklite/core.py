@@ -166,6 +166,30 @@ def _executor_main(index, conn, app_dir, conf, env):
       os._exit(0)
 
   signal.signal(signal.SIGTERM, _on_term)
+
+  # A driver that is killed (SIGKILL, `timeout`, OOM) cannot stop its executors, and the pipe gives
+  # no EOF because every later-forked sibling inherited a copy of its driver-side end.  Executors
+  # lead their own session, so nothing else reaps them either: watch the parent pid instead.
+  driver_pid = os.getppid()
+
+  def _watch_driver():
+    import time as _time
+    while True:
+      _time.sleep(1.0)
+      if os.getppid() != driver_pid:
+        try:
+          from .. import shmring
+          shmring.run_cleanups()
+        except Exception:
+          pass
+        try:
+          if os.getpgid(0) == os.getpid():
+            os.killpg(os.getpid(), signal.SIGTERM)   # node processes of this executor too
+        except Exception:
+          pass
+        os._exit(0)
+
+  threading.Thread(target=_watch_driver, name="sparklite-driver-watch", daemon=True).start()
   cwd = os.path.join(app_dir, "executor-{}".format(index))
   os.makedirs(cwd, exist_ok=True)
   os.chdir(cwd)

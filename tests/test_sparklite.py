@@ -91,3 +91,43 @@ def test_streaming_queue(sc):
   assert not ssc.awaitTerminationOrTimeout(1.0)
   ssc.stop(stopSparkContext=False, stopGraceFully=True)
   assert sorted(got) == [1, 2, 3]
+
+
+def test_executors_do_not_outlive_a_killed_driver(tmp_path):
+  """kill -9 of the driver must not leave executor processes (and their node children) behind."""
+  import os
+  import signal
+  import subprocess
+  import sys
+  import time
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  pidfile = str(tmp_path / "pids")
+  code = (
+      "import os, sys, time\n"
+      "sys.path.insert(0, {root!r})\n"
+      "from tensorflowonspark_b200.sparklite import SparkContext\n"
+      "sc = SparkContext('local[2]', 'orphan-test')\n"
+      "pids = sc.parallelize(range(2), 2).map(lambda _: os.getpid()).collect()\n"
+      "open({pidfile!r}, 'w').write(' '.join(map(str, pids)))\n"
+      "time.sleep(600)\n").format(root=root, pidfile=pidfile)
+  drv = subprocess.Popen([sys.executable, "-c", code])
+  deadline = time.time() + 60
+  while not os.path.exists(pidfile) and time.time() < deadline:
+    time.sleep(0.2)
+  time.sleep(0.3)
+  pids = [int(p) for p in open(pidfile).read().split()]
+  assert len(set(pids)) == 2
+  os.kill(drv.pid, signal.SIGKILL)
+  drv.wait()
+
+  def alive(pid):
+    try:
+      os.kill(pid, 0)
+      return open("/proc/{}/stat".format(pid)).read().split(") ")[1][0] != "Z"
+    except (OSError, IOError):
+      return False
+
+  deadline = time.time() + 15
+  while any(alive(p) for p in pids) and time.time() < deadline:
+    time.sleep(0.3)
+  assert not any(alive(p) for p in pids), "executors survived their driver: {}".format(pids)
