@@ -94,11 +94,19 @@ class TFNodeContext(object):
     from .parallel import process_group
     return process_group.init_from_ctx(self, backend=backend, timeout_s=timeout_s)
 
-  def symmetric_comm(self):
+  def symmetric_comm(self, ranks=None):
     """Peer-mapped memory + flag barriers across the worker GPUs (parallel/symm.py); the IPC
-    handles are exchanged over the reservation server's key/value board."""
+    handles are exchanged over the reservation server's key/value board.  ``ranks``: restrict the
+    communicator to a sub-group of worker ranks (every member must make the same call) - the hook
+    for layering tensor / sequence / context-parallel groups on the launcher later."""
     from .parallel import process_group
-    return process_group.symm_from_ctx(self)
+    return process_group.symm_from_ctx(self, ranks)
+
+  def new_group(self, ranks, backend=None):
+    """A torch.distributed sub-group of worker ranks (collective: every rank of the job calls it,
+    as torch requires); returns the group, or None on ranks outside it."""
+    from .parallel import process_group
+    return process_group.new_group(self, ranks, backend)
 
 
 class TFSparkNode(object):

@@ -36,16 +36,40 @@ def init_from_ctx(ctx, backend=None, timeout_s=1800):
   return dist.group.WORLD
 
 
-def symm_from_ctx(ctx):
-  """SymmComm whose handle exchange runs over the reservation server's key/value board."""
+def new_group(ctx, ranks, backend=None):
+  """torch.distributed.new_group over ``ranks`` (the default group is joined first if needed)."""
+  import torch.distributed as dist
+  if not dist.is_initialized():
+    init_from_ctx(ctx)
+  ranks = sorted(set(int(r) for r in ranks))
+  if not ranks or ranks[0] < 0 or ranks[-1] >= ctx.world_size:
+    raise ValueError("ranks {} outside the job's 0..{}".format(ranks, ctx.world_size - 1))
+  g = dist.new_group(ranks=ranks, backend=backend)
+  return g if ctx.rank in ranks else None
+
+
+def symm_from_ctx(ctx, ranks=None):
+  """SymmComm whose handle exchange runs over the reservation server's key/value board.
+  ``ranks`` (optional): a sub-group of worker ranks; the communicator's rank / world are then the
+  position in / size of that group, and its exchanges use a board namespace of their own."""
   from .. import reservation
   from . import symm
+  if ranks is None:
+    members = list(range(ctx.world_size))
+  else:
+    members = sorted(set(int(r) for r in ranks))
+    if ctx.rank not in members:
+      raise ValueError("rank {} is not a member of the group {}".format(ctx.rank, members))
+    if members[0] < 0 or members[-1] >= ctx.world_size:
+      raise ValueError("ranks {} outside the job's 0..{}".format(members, ctx.world_size - 1))
+  me, size = members.index(ctx.rank), len(members)
+  scope = "all" if ranks is None else "-".join(str(r) for r in members)
   client = reservation.Client(ctx.server_addr)
   counter = [0]
 
   def exchange(obj):
     counter[0] += 1
-    tag = "symm/{}/{}".format(ctx.cluster_id, counter[0])
-    return client.all_gather(tag, ctx.rank, ctx.world_size, obj)
+    tag = "symm/{}/{}/{}".format(ctx.cluster_id, scope, counter[0])
+    return client.all_gather(tag, me, size, obj)
 
-  return symm.SymmComm(ctx.rank, ctx.world_size, exchange, ctx.device)
+  return symm.SymmComm(me, size, exchange, ctx.device)

@@ -145,3 +145,49 @@ def test_argv_list_becomes_sys_argv(sc):
     assert sys.argv == ["prog", "--flag", "1"] and argv == sys.argv
 
   TFCluster.run(sc, fn, ["prog", "--flag", "1"], 2, 0).shutdown()
+
+
+def test_subgroups_process_group_and_board_namespaces(sc, monkeypatch):
+  """ctx.new_group (torch.distributed sub-group) and the sub-group flavour of the symmetric-memory
+  bootstrap (rank / world remapped, board namespace per group) - the hooks for TP/SP/CP groups."""
+  import tempfile
+  d = tempfile.mkdtemp()
+
+  def fn(args, ctx):
+    import json
+    import torch
+    import torch.distributed as dist
+    from tensorflowonspark_b200.parallel import process_group, symm
+    ctx.init_process_group(backend="gloo")
+    g = ctx.new_group([0, 1])
+    t = torch.tensor([float(ctx.rank + 1)])
+    dist.all_reduce(t, group=g)
+    solo = ctx.new_group([1])              # collective call on both ranks, member on one
+    seen = {}
+
+    class FakeComm(object):                # the CUDA-IPC part needs a GPU: capture the bootstrap
+      def __init__(self, rank, world, exchange, device):
+        seen.update(rank=rank, world=world, gathered=exchange({"r": ctx.rank}))
+
+    real, symm.SymmComm = symm.SymmComm, FakeComm
+    try:
+      process_group.symm_from_ctx(ctx, ranks=[0, 1])
+      pair = dict(seen)
+      process_group.symm_from_ctx(ctx, ranks=[ctx.rank])
+      alone = dict(seen)
+    finally:
+      symm.SymmComm = real
+    with open("{}/{}".format(args["d"], ctx.rank), "w") as f:
+      json.dump({"sum": float(t), "solo_member": solo is not None, "pair": pair, "alone": alone}, f)
+
+  cluster = TFCluster.run(sc, fn, {"d": d}, 2, 0, input_mode=TFCluster.InputMode.TENSORFLOW,
+                          master_node="chief")
+  cluster.shutdown()
+  import json
+  res = [json.load(open("{}/{}".format(d, r))) for r in range(2)]
+  assert [r["sum"] for r in res] == [3.0, 3.0]
+  assert [r["solo_member"] for r in res] == [False, True]
+  for r, rec in enumerate(res):
+    assert rec["pair"]["rank"] == r and rec["pair"]["world"] == 2
+    assert [x["r"] for x in rec["pair"]["gathered"]] == [0, 1]
+    assert rec["alone"] == {"rank": 0, "world": 1, "gathered": [{"r": r}]}
