@@ -20,6 +20,12 @@ os.environ["PATH"] = _FAKE_DIR + os.pathsep + os.environ.get("PATH", "")
 os.environ["TFOS_HEARTBEAT_TIMEOUT"] = "3"   # likewise inherited by the executors at fork time
 
 
+@pytest.fixture(scope="module", autouse=True)
+def _heartbeat_env_only_for_this_module():
+  yield
+  os.environ.pop("TFOS_HEARTBEAT_TIMEOUT", None)   # later modules fork their executors without it
+
+
 def _alive(pid):
   try:
     os.kill(pid, 0)
