@@ -66,3 +66,37 @@ def test_ring_pack_unpack_roundtrip(nrows, colspecs, seed):
     ring.release_read(blk.pos)
   finally:
     shmring._unlink(name)
+
+
+@settings(max_examples=200, deadline=None)
+@given(st.integers(1, 120), st.integers(1, 120), st.integers(1, 64),
+       st.sampled_from([(1, False, 128, 1), (16, True, 128, 1), (16, True, 64, 64)]))
+def test_choose_box_covers_the_tensor_within_the_mma_limits(OW, OH, N, mode):
+  """The pixel-box planner of the implicit-GEMM kernels (pure python, no GPU): the box fits the
+  MMA's 128 (or 64) rows, respects the K granularity of the weight-gradient kernels, and the
+  tile grid covers every pixel."""
+  from tensorflowonspark_b200.ops import igemm
+  multiple_of, allow_pad, max_rows, min_rows = mode
+  try:
+    bw, bh, bn, tw, th, tn = igemm.choose_box(OW, OH, N, multiple_of=multiple_of,
+                                              allow_pad=allow_pad, max_rows=max_rows,
+                                              min_rows=min_rows)
+  except ValueError:
+    assert not allow_pad          # without padding some extents have no 16-row-multiple box
+    return
+  rows = bw * bh * bn
+  assert 1 <= rows <= max_rows and rows % multiple_of == 0 and rows >= min_rows
+  assert tw * bw >= OW and th * bh >= OH and tn * bn >= N          # full coverage
+  assert (tw - 1) * bw < OW and (th - 1) * bh < OH and (tn - 1) * bn < N   # no empty tiles
+  if not allow_pad:
+    assert bw <= OW and bh <= OH
+  if bn > 1:
+    assert tw == 1 and th == 1    # images are batched into a box only when one box holds a whole image
+
+
+def test_stem_geometry_matches_a_7x7_stride2_pad3_convolution():
+  from tensorflowonspark_b200.ops import igemm
+  for hw in (32, 64, 65, 224, 225):
+    OH, OW, Wp = igemm.stem_geometry(hw, hw)
+    assert OH == (hw + 6 - 7) // 2 + 1 == OW
+    assert Wp % 2 == 0 and Wp >= hw + 4 and Wp >= 2 * (OW - 1) + 8   # last window stays in the row
