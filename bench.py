@@ -36,7 +36,9 @@ def parse_args():
   p.add_argument("--gpus", type=int, default=1)
   p.add_argument("--steps", type=int, default=20)
   p.add_argument("--warmup", type=int, default=5)
-  p.add_argument("--impl", default="ours")
+  p.add_argument("--impl", default="ours", choices=["ours", "reference", "nccl-cudnn"],
+                 help="ours | reference (the unmodified reference: unavailable on this image) | "
+                      "nccl-cudnn (stock torchvision + cuDNN + DDP/NCCL comparator, same contract)")
   p.add_argument("--batch", type=int, default=int(os.environ.get("TFOS_BENCH_BATCH", "256")),
                  help="per-GPU batch")
   p.add_argument("--image", type=int, default=224)
@@ -95,6 +97,19 @@ class ClockSampler(object):
             "samples": len(sm), "power_w_max": max(power) if power else None}
 
 
+def measured_baseline(n_gpus, key="value"):
+  """Same-box NCCL + cuDNN comparator numbers (baseline/nccl_cudnn_measured.json, written from
+  `bench.py --impl nccl-cudnn` runs on the B200 pod).  The reference
+  publishes no numbers, so this is the BASELINE.md figure `vs_baseline` divides by."""
+  try:
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "baseline",
+                           "nccl_cudnn_measured.json")) as f:
+      rec = json.load(f)["images_per_s"].get(str(n_gpus))
+    return float(rec[key]) if rec and rec.get(key) else None
+  except Exception:
+    return None
+
+
 def reference_arm(args):
   # The unmodified reference needs pyspark + a JVM + tensorflow; none is installed and there is
   # no network.  `pip install --no-index --target baseline/_ref /root/reference` also fails at
@@ -151,6 +166,10 @@ def main():
   args = parse_args()
   if args.impl == "reference":
     return reference_arm(args)
+  if args.impl == "nccl-cudnn":
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "baseline"))
+    import nccl_cudnn_resnet50
+    return nccl_cudnn_resnet50.run(args, ClockSampler)
 
   import torch
   rank = int(os.environ.get("RANK", "0"))
@@ -229,10 +248,12 @@ def main():
   ms_max = float(t)
   ms_per_step = ms_max / args.steps
   value = B * world * args.steps / (ms_max / 1e3)
+  base = measured_baseline(world)
   watchdog.partial = {
       "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
       "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
-      "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "impl": "ours",
+      "scaling": "weak", "vs_baseline": (value / base) if base else None, "dtype": "bf16",
+      "impl": "ours",
       "data": "synthetic (uint8 224x224x3 ImageNet-shaped, random-init weights)",
       "config": {"model": "resnet50_v1.5", "global_batch": B * world, "per_gpu_batch": B,
                  "image": args.image, "parallelism": "dp{}".format(world)},
@@ -304,7 +325,11 @@ def main():
     out = {
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": (value / base) if base else None, "dtype": "bf16",
+        "baseline": {"what": "stock torchvision + cuDNN + DDP/NCCL on the same pod "
+                             "(bench.py --impl nccl-cudnn; BASELINE.md section 4)",
+                     "images_per_s": base, "e2e_images_per_s": measured_baseline(world, "e2e")},
         "data": "synthetic (uint8 224x224x3 ImageNet-shaped, random-init weights)",
         "impl": "ours",
         "config": {"model": "resnet50_v1.5", "global_batch": B * world, "per_gpu_batch": B,
@@ -317,6 +342,8 @@ def main():
         "launches_per_step": launches_per_step, "final_loss": loss,
     }
     if e2e is not None:
+      be = measured_baseline(world, "e2e")
+      e2e["vs_baseline"] = (e2e["value"] / be) if be else None
       out["e2e"] = e2e
     if exposed is not None:
       out["exposed_allreduce_ms_per_step"] = exposed

@@ -335,10 +335,14 @@ def batchnorm():
       K.bn_bwd_reduce(dy, x, bits, mean, invstd, d3, b3, 3, None, None)
       K.bn_bwd_apply(dy, x, bits, gamma, mean, invstd, d3, b3, dx3, dres3, 3, None, None)
       torch.cuda.synchronize()
-      ok &= _report("bn bitmask fwd", _rel(y3, y), 1e-9)
-      ok &= _report("bn bitmask dgamma", _rel(d3, dgamma), 1e-5)
-      ok &= _report("bn bitmask dx", _rel(dx3, dx), 2e-3)  # dgamma: atomic order
-      ok &= _report("bn bitmask dres", _rel(dres3, dres), 1e-9)
+      # every mode is held to the fp32 PyTorch reference (dgamma/dbeta are summed with atomics,
+      # so two kernel runs may differ in the last bits: never compare kernel against kernel)
+      ok &= _report("bn bitmask fwd", _rel(y3, yr), 2e-2)
+      ok &= _report("bn bitmask == stored-y mask", float((y3 != y).sum()), 0.5)
+      ok &= _report("bn bitmask dgamma", _rel(d3, g32.grad), 2e-2)
+      ok &= _report("bn bitmask dbeta", _rel(b3, b32.grad), 2e-2)
+      ok &= _report("bn bitmask dx", _rel(dx3, xf.grad), 3e-2)
+      ok &= _report("bn bitmask dres", _rel(dres3, dy.float() * mask), 2e-2)
     # finalisation folded into the apply kernel == bn_finalize + bn_apply
     if C % 8 == 0:
       s2, ss2 = z(), z()
@@ -350,10 +354,15 @@ def batchnorm():
       torch.cuda.synchronize()
       # (the two runs sum the statistics with atomics in different orders: last-bit differences
       # in the mean, hence the odd bf16 rounding flip in y)
-      ok &= _report("bn fused finalize: y", _rel(y4, y), 1e-2)
-      ok &= _report("bn fused finalize: mean/invstd", _rel(m2, mean) + _rel(is2, invstd), 1e-5)
-      ok &= _report("bn fused finalize: scale/shift", _rel(sc2, scale) + _rel(sh2, shift), 1e-5)
-      ok &= _report("bn fused finalize: running stats", _rel(rm2, rm) + _rel(rv2, rv), 1e-5)
+      ok &= _report("bn fused finalize: y", _rel(y4, yr), 2e-2)
+      ok &= _report("bn fused finalize: mean", _rel(m2, m), 1e-3)
+      ok &= _report("bn fused finalize: invstd", _rel(is2, 1.0 / torch.sqrt(v + 1e-5)), 1e-3)
+      sc_ref = gamma / torch.sqrt(v + 1e-5)
+      ok &= _report("bn fused finalize: scale", _rel(sc2, sc_ref), 1e-3)
+      ok &= _report("bn fused finalize: shift", _rel(sh2, beta - m * sc_ref), 1e-3)
+      ok &= _report("bn fused finalize: running mean", _rel(rm2, 0.1 * m), 1e-3)
+      ok &= _report("bn fused finalize: running var",
+                    _rel(rv2, 0.9 + 0.1 * xf.detach().var(0, unbiased=True)), 1e-3)
     # no-residual unit: ReLU mask recomputed from x (mode 2) must match the stored-y mask (mode 1)
     y2 = torch.empty_like(x)
     K.bn_apply(x, None, scale, shift, y2, 1)
@@ -364,9 +373,20 @@ def batchnorm():
     K.bn_bwd_reduce(dy, x, None, mean, invstd, d2, b2, 2, scale, shift)
     K.bn_bwd_apply(dy, x, None, gamma, mean, invstd, d2, b2, dx2, None, 2, scale, shift)
     torch.cuda.synchronize()
-    ok &= _report("bn mask-recompute dgamma", _rel(d2, d1), 1e-4)
+    xg = x.float().requires_grad_(True)
+    g2, bb2 = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    torch.relu((xg - m.detach()) / torch.sqrt(v.detach() + 1e-5) * g2 + bb2).backward(dy.float())
+    # (reference with mean/var held constant gives the parameter gradients; dx needs the full
+    # graph, so it is checked against autograd through the batch statistics below)
+    ok &= _report("bn mask-from-y dgamma", _rel(d1, g2.grad), 2e-2)
+    ok &= _report("bn mask-recompute dgamma", _rel(d2, g2.grad), 2e-2)
+    ok &= _report("bn mask-recompute dbeta", _rel(b2, bb2.grad), 2e-2)
+    xh = x.float().requires_grad_(True)
+    mh, vh = xh.mean(0), xh.var(0, unbiased=False)
+    torch.relu((xh - mh) / torch.sqrt(vh + 1e-5) * gamma + beta).backward(dy.float())
     # a pre-activation within one rounding of zero may flip its mask (FMA vs mul+add): 1 element
-    ok &= _report("bn mask-recompute dx", _rel(dx2, dx1), 1e-2)
+    ok &= _report("bn mask-from-y dx", _rel(dx1, xh.grad), 3e-2)
+    ok &= _report("bn mask-recompute dx", _rel(dx2, xh.grad), 3e-2)
   return ok
 
 
