@@ -314,15 +314,17 @@ __global__ void __launch_bounds__(256)
 ps_push_dense_kernel(float* __restrict__ w_ps, const float* __restrict__ g, long long n,
                      const float* __restrict__ hyper) {
   const float k = -hyper[0] * hyper[3];
+  // (a row cut by a server boundary arrives here with an arbitrary element offset)
+  const bool vec = ((reinterpret_cast<uintptr_t>(w_ps) | reinterpret_cast<uintptr_t>(g)) & 15) == 0;
   for (long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x * 4) {
-    if (i + 4 <= n) {
+    if (vec && i + 4 <= n) {
       const float4 v = *reinterpret_cast<const float4*>(g + i);
       asm volatile("red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(w_ps + i),
                    "f"(k * v.x), "f"(k * v.y), "f"(k * v.z), "f"(k * v.w)
                    : "memory");
     } else {
-      for (long long j = i; j < n; ++j)
+      for (long long j = i; j < min(n, i + 4); ++j)
         asm volatile("red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(w_ps + j), "f"(k * g[j])
                      : "memory");
     }

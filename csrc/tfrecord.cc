@@ -146,12 +146,19 @@ struct Reader {
     p += n;
     return r;
   }
+  // advance over a fixed-width field; a record that ends inside it is malformed
+  const uint8_t* fixed(int n) {
+    if (static_cast<int64_t>(e - p) < n) throw std::runtime_error("truncated fixed-width field in Example");
+    const uint8_t* q = p;
+    p += n;
+    return q;
+  }
   void skip(int wt) {
     switch (wt) {
       case 0: varint(); break;
-      case 1: p += 8; break;
+      case 1: fixed(8); break;
       case 2: sub(); break;
-      case 5: p += 4; break;
+      case 5: fixed(4); break;
       default: throw std::runtime_error("unsupported wire type in Example");
     }
   }
@@ -242,6 +249,7 @@ py::dict decode_example(const py::bytes& data) {
                 continue;
               }
               if (kf == 1) {
+                if (wt5 != 2) throw std::runtime_error("BytesList value with a non-bytes wire type");
                 Reader b = lst.sub();
                 values.append(py::bytes(reinterpret_cast<const char*>(b.p), b.e - b.p));
               } else if (kf == 2) {
@@ -252,18 +260,21 @@ py::dict decode_example(const py::bytes& data) {
                     std::memcpy(&f, q, 4);
                     values.append(f);
                   }
-                } else {
+                } else if (wt5 == 5) {
                   float f;
-                  std::memcpy(&f, lst.p, 4);
-                  lst.p += 4;
+                  std::memcpy(&f, lst.fixed(4), 4);
                   values.append(f);
+                } else {
+                  throw std::runtime_error("FloatList value with a non-float wire type");
                 }
               } else {
                 if (wt5 == 2) {
                   Reader pk = lst.sub();
                   while (!pk.done()) values.append(static_cast<int64_t>(pk.varint()));
-                } else {
+                } else if (wt5 == 0) {
                   values.append(static_cast<int64_t>(lst.varint()));
+                } else {
+                  throw std::runtime_error("Int64List value with a non-varint wire type");
                 }
               }
             }

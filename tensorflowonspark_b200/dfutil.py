@@ -37,29 +37,28 @@ def isLoadedDF(df):
   return id(df) in loadedDF and loadedDF[id(df)][0] is df
 
 
-def _local(path):
-  return path[len("file://"):] if path.startswith("file://") else path
+TFRECORD_INPUT_FORMAT = "org.tensorflow.hadoop.io.TFRecordFileInputFormat"
+TFRECORD_OUTPUT_FORMAT = "org.tensorflow.hadoop.io.TFRecordFileOutputFormat"
+_KEY_CLASS = "org.apache.hadoop.io.BytesWritable"
+_VALUE_CLASS = "org.apache.hadoop.io.NullWritable"
 
 
 def saveAsTFRecords(df, output_dir):
-  """Write a DataFrame as TFRecord files (one ``part-r-NNNNN`` per partition) of Examples."""
-  out = _local(output_dir)
-  if os.path.exists(out):
-    raise IOError("Output directory {} already exists".format(output_dir))
-  os.makedirs(out)
-  encode = toTFExample(df.dtypes)
+  """Write a DataFrame as TFRecord files (one ``part-r-NNNNN`` per partition) of Examples.
 
-  def write(index, it):
-    path = os.path.join(out, "part-r-{:05d}".format(index))
-    tfrecord.write_records(path, [bytes(rec) for rec, _ in encode(it)])
-    return iter([])
-
-  df.rdd.mapPartitionsWithIndex(write).count()
-  open(os.path.join(out, "_SUCCESS"), "w").close()
+  Goes through ``RDD.saveAsNewAPIHadoopFile`` with the tensorflow-hadoop output format, exactly
+  like the reference (dfutil.py:29-41): under real pyspark the Hadoop layer resolves
+  ``hdfs://`` / ``viewfs://`` paths and writes on the executors' shared filesystem; under
+  sparklite the same call lands in the native TFRecord writer on the local filesystem."""
+  tf_rdd = df.rdd.mapPartitions(toTFExample(df.dtypes))
+  tf_rdd.saveAsNewAPIHadoopFile(output_dir, TFRECORD_OUTPUT_FORMAT, keyClass=_KEY_CLASS,
+                                valueClass=_VALUE_CLASS)
 
 
 def loadTFRecords(sc, input_dir, binary_features=[], schema_hint=None):
-  """Load TFRecord files of Examples as a DataFrame.
+  """Load TFRecord files of Examples as a DataFrame (``sc.newAPIHadoopFile`` with the
+  tensorflow-hadoop input format, reference dfutil.py:44-80 - any filesystem the bound Spark
+  backend can read).
 
   The schema is inferred from the first record (a feature holding one value becomes a scalar
   column, several values an array column); ``binary_features`` lists bytes features that must
@@ -67,26 +66,16 @@ def loadTFRecords(sc, input_dir, binary_features=[], schema_hint=None):
   ``struct<...>`` string) overrides the inference for the named columns - the Scala-side
   capability (DFUtil.scala:35-55).
   """
-  from .sparklite import core as _core
-  src = _local(input_dir)
-  files = [f for f in _core._list_files(src)]
-  if not files:
-    raise IOError("no TFRecord files under {}".format(input_dir))
-  rdd = sc.parallelize(files, len(files)).flatMap(lambda f: tfrecord.read_records(f))
-  first = tfrecord.read_records(files[0])
+  tfr_rdd = sc.newAPIHadoopFile(input_dir, TFRECORD_INPUT_FORMAT, keyClass=_KEY_CLASS,
+                                valueClass=_VALUE_CLASS)
+  first = tfr_rdd.take(1)
   if not first:
-    raise IOError("{} holds no records".format(files[0]))
+    raise IOError("no TFRecord records under {}".format(input_dir))
   hint = parse_schema(schema_hint) if isinstance(schema_hint, str) else schema_hint
-  schema = infer_schema(first[0], binary_features, hint)
+  schema = infer_schema(bytes(first[0][0]), binary_features, hint)
   names = schema.names
-  rows = rdd.mapPartitions(lambda it: fromTFExample(it, binary_features, schema))
-  try:
-    from .sparklite.sql import SparkSession
-    spark = SparkSession.builder.getOrCreate()
-  except Exception:  # pragma: no cover
-    from pyspark.sql import SparkSession
-    spark = SparkSession.builder.getOrCreate()
-  df = spark.createDataFrame(rows.map(lambda r: tuple(r[n] for n in names)), schema)
+  rows = tfr_rdd.mapPartitions(lambda it: fromTFExample(it, binary_features, schema))
+  df = rows.map(lambda r: tuple(r[n] for n in names)).toDF(schema)
   loadedDF[id(df)] = (df, input_dir)
   return df
 

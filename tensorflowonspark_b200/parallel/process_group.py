@@ -48,6 +48,12 @@ def new_group(ctx, ranks, backend=None):
   return g if ctx.rank in ranks else None
 
 
+# communicators created so far in this process, per (cluster, scope): every member creates its
+# communicators in the same order (it is a collective), so the generation number agrees across
+# ranks and keeps the board tags of two communicators of one job apart
+_generations = {}
+
+
 def symm_from_ctx(ctx, ranks=None):
   """SymmComm whose handle exchange runs over the reservation server's key/value board.
   ``ranks`` (optional): a sub-group of worker ranks; the communicator's rank / world are then the
@@ -66,10 +72,14 @@ def symm_from_ctx(ctx, ranks=None):
   scope = "all" if ranks is None else "-".join(str(r) for r in members)
   client = reservation.Client(ctx.server_addr)
   counter = [0]
+  gen = _generations[(ctx.cluster_id, scope)] = _generations.get((ctx.cluster_id, scope), 0) + 1
 
   def exchange(obj):
+    # unique per communicator (generation) and per exchange (counter); the board entries are
+    # consumed by the all_gather itself, so even a re-created process that restarts its
+    # generation count cannot read a peer's stale (possibly freed) IPC handle
     counter[0] += 1
-    tag = "symm/{}/{}/{}".format(ctx.cluster_id, scope, counter[0])
+    tag = "symm/{}/{}/g{}/{}".format(ctx.cluster_id, scope, gen, counter[0])
     return client.all_gather(tag, me, size, obj)
 
   return symm.SymmComm(me, size, exchange, ctx.device)

@@ -161,7 +161,8 @@ class PSClient(object):
       a -= (lr * scale) * g[p["lo"]:p["hi"]]
 
   def push_sparse(self, grad_rows, indices, width, base=0, lr=1.0, scale=1.0):
-    """Row-sparse update of a [rows, width] table stored at flat offset ``base``."""
+    """Row-sparse update of a [rows, width] table stored at flat offset ``base``.  A row that
+    straddles a server boundary is split: each server applies the elements it owns."""
     if self.cuda:
       import torch
       from .. import ops
@@ -172,19 +173,30 @@ class PSClient(object):
         lo, hi = p["lo"], p["hi"]
         r0, r1 = max(0, (lo - base + width - 1) // width), max(0, (hi - base) // width)
         sel = (idx >= r0) & (idx < r1)
-        if bool(sel.any()):
+        if r1 > r0 and bool(sel.any()):
           rows = grad_rows[sel].contiguous()
           local = (idx[sel] - r0).contiguous()
           off = base + r0 * width - lo
           ops.K.ps_push_sparse(ptr + 4 * off, rows, local, self.hyper)
+        # rows cut by this server's boundaries: the owned element range goes through the dense kernel
+        for edge in (lo, hi):
+          r = (edge - base) // width
+          s0 = base + r * width
+          if edge <= base or s0 == edge or s0 + width <= lo or s0 >= hi:
+            continue
+          a, b = max(s0, lo), min(s0 + width, hi)
+          for k in torch.nonzero(idx == r).flatten().tolist():
+            seg = grad_rows[k].reshape(-1)[a - s0:b - s0].to(torch.float32).contiguous()
+            ops.K.ps_push_dense(ptr + 4 * (a - lo), seg, self.hyper)
       return
     g = grad_rows.detach().cpu().numpy() if hasattr(grad_rows, "detach") else np.asarray(grad_rows)
     ix = indices.detach().cpu().numpy() if hasattr(indices, "detach") else np.asarray(indices)
     for p, a in zip(self.parts, self.arrays):
       for row, r in zip(g, ix):
         s = base + int(r) * width
-        if p["lo"] <= s and s + width <= p["hi"]:
-          a[s - p["lo"]:s - p["lo"] + width] -= (lr * scale) * row
+        b0, b1 = max(s, p["lo"]), min(s + width, p["hi"])   # the part of the row this server owns
+        if b0 < b1:
+          a[b0 - p["lo"]:b1 - p["lo"]] -= (lr * scale) * row[b0 - s:b1 - s]
 
   def close(self):
     if self.cuda:

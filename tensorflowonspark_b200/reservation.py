@@ -96,6 +96,7 @@ class Server(MessageSocket):
     self.reservations = Reservations(count)
     self.done = False
     self._board = {}
+    self._fetches = {}
     self._board_lock = threading.Lock()
     self._sock = None
 
@@ -176,8 +177,26 @@ class Server(MessageSocket):
         self._board[msg["key"]] = msg["data"]
       self.send(sock, "OK")
     elif kind == "GET":
+      # ``consume`` = n: the key is dropped after it has been fetched n times (a collective in
+      # which every rank reads every key once leaves nothing behind, so a later collective that
+      # reuses the tag - a re-created communicator, a retried task - cannot see stale data)
+      key, consume = msg["key"], int(msg.get("consume") or 0)
       with self._board_lock:
-        self.send(sock, {"found": msg["key"] in self._board, "data": self._board.get(msg["key"])})
+        found = key in self._board
+        data = self._board.get(key)
+        if found and consume > 0:
+          n = self._fetches.get(key, 0) + 1
+          if n >= consume:
+            del self._board[key]
+            self._fetches.pop(key, None)
+          else:
+            self._fetches[key] = n
+      self.send(sock, {"found": found, "data": data})
+    elif kind == "DEL":
+      with self._board_lock:
+        self._board.pop(msg["key"], None)
+        self._fetches.pop(msg["key"], None)
+      self.send(sock, "OK")
     else:
       self.send(sock, "ERR")
 
@@ -260,11 +279,16 @@ class Client(MessageSocket):
   def put(self, key, data):
     return self._request("PUT", key=key, data=data)
 
-  def get(self, key, timeout=600):
+  def delete(self, key):
+    return self._request("DEL", key=key)
+
+  def get(self, key, timeout=600, consume=0):
+    """Poll the board for ``key``.  ``consume`` = n: the server forgets the key once n fetches
+    have succeeded (used by :meth:`all_gather`, where each of n ranks reads every key once)."""
     t0 = time.time()
     delay = 0.01
     while True:
-      r = self._request("GET", key=key)
+      r = self._request("GET", key=key, consume=consume)
       if r["found"]:
         return r["data"]
       if time.time() - t0 > timeout:
@@ -273,9 +297,11 @@ class Client(MessageSocket):
       delay = min(0.5, delay * 1.5)
 
   def all_gather(self, tag, rank, world, data, timeout=600):
-    """Collective over the board: every rank contributes ``data``, gets the list of all."""
+    """Collective over the board: every rank contributes ``data``, gets the list of all.  The
+    entries are consumed: after the last rank has read them the board holds nothing under
+    ``tag``, so the tag can be reused safely."""
     self.put("{}/{}".format(tag, rank), data)
-    return [self.get("{}/{}".format(tag, r), timeout) for r in range(world)]
+    return [self.get("{}/{}".format(tag, r), timeout, consume=world) for r in range(world)]
 
   def close(self):
     try:

@@ -16,6 +16,7 @@ stages that need all slots at once, ``statusTracker`` active-task counts, task
 failures surfacing on the driver.
 """
 import glob as _glob
+import re as _re
 import itertools
 import logging
 import multiprocessing
@@ -684,6 +685,10 @@ def _strip_scheme(path):
   for scheme in ("file://",):
     if path.startswith(scheme):
       return path[len(scheme):] or "/"
+  m = _re.match(r"^([a-zA-Z][a-zA-Z0-9+.-]*)://", path)
+  if m:  # hdfs://, viewfs://, s3a:// ...: fail loudly instead of creating a local "hdfs:" directory
+    raise IOError("sparklite only reads and writes the local filesystem (file://); '{}' needs a "
+                  "real Spark/Hadoop backend (install pyspark)".format(path))
   return path
 
 

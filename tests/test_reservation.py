@@ -91,3 +91,51 @@ def test_await_timeout():
   with pytest.raises(Exception):
     s.await_reservations(timeout=1)
   s.stop()
+
+
+def test_all_gather_consumes_its_keys_so_a_tag_can_be_reused():
+  """a second communicator must never read the first one's (stale) entries."""
+  n = 3
+  s = Server(1)
+  addr = s.start()
+  out = {}
+
+  def run(rank, rnd):
+    c = Client(addr)
+    out[(rnd, rank)] = c.all_gather("symm/job/all/g1/1", rank, n, {"handle": "r{}-round{}".format(rank, rnd)})
+    c.close()
+
+  for rnd in (1, 2):   # same tag twice, e.g. a re-created process that restarted its counters
+    ts = [threading.Thread(target=run, args=(r, rnd)) for r in range(n)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    for r in range(n):
+      assert [d["handle"] for d in out[(rnd, r)]] == ["r{}-round{}".format(k, rnd) for k in range(n)]
+    assert s._board == {} and s._fetches == {}
+  s.stop()
+
+
+def test_two_communicators_of_one_job_use_distinct_board_tags():
+  from tensorflowonspark_b200.parallel import process_group, symm
+  tags = []
+
+  class FakeClient(object):
+    def __init__(self, addr):
+      pass
+
+    def all_gather(self, tag, me, size, obj):
+      tags.append(tag)
+      return [obj]
+
+  class Ctx(object):
+    world_size, rank, cluster_id, server_addr, device = 1, 0, "job42", ("127.0.0.1", 1), "cpu"
+
+  made = []
+  with mock.patch("tensorflowonspark_b200.reservation.Client", FakeClient), \
+      mock.patch.object(symm, "SymmComm", lambda me, size, exchange, dev: made.append(exchange)):
+    process_group.symm_from_ctx(Ctx())
+    process_group.symm_from_ctx(Ctx())
+  made[0]({"a": 1})
+  made[1]({"a": 1})
+  made[0]({"a": 2})
+  assert len(set(tags)) == 3 and all(t.startswith("symm/job42/all/g") for t in tags)
