@@ -89,6 +89,11 @@ class Trainer(object):
     else:
       self.model.load_state_dict(sd)
 
+  def served_model(self):
+    """The object whose ``export_builder`` rebuilds this model for serving (checkpoint.save(...,
+    model=...) records it so TFModel can serve the newest checkpoint of a model_dir)."""
+    return self.net if self.native else self.model
+
   def export(self, export_dir, is_chief):
     from tensorflowonspark_b200 import compat
     compat.export_saved_model(self.net if self.native else self.model, export_dir, is_chief,

@@ -84,20 +84,29 @@ class TFCluster(object):
     workers = [n for n in self.cluster_info if n["job_name"] not in ("ps", "evaluator")]
 
     armed = False
+    timer = None
+
+    def on_alarm(signum=None, frame=None):
+      logger.error("TensorFlow execution timed out, exiting Spark application with error status")
+      self.sc.cancelAllJobs()
+      self.sc.stop()
+      if signum is None:     # timer thread: sys.exit would only end this thread
+        os._exit(1)
+      sys.exit(1)
+
     if timeout > 0 and threading.current_thread() is threading.main_thread():
-
-      def on_alarm(signum, frame):
-        logger.error("TensorFlow execution timed out, exiting Spark application with error status")
-        self.sc.cancelAllJobs()
-        self.sc.stop()
-        sys.exit(1)
-
       try:
         signal.signal(signal.SIGALRM, on_alarm)
         signal.alarm(int(timeout))
         armed = True
       except (ValueError, AttributeError):
         pass
+    if timeout > 0 and not armed:
+      # signals can only be installed from the main thread (reference TFCluster.py:125-136 assumes
+      # it): a shutdown driven from another thread gets the same watchdog from a timer thread
+      timer = threading.Timer(float(timeout), on_alarm)
+      timer.daemon = True
+      timer.start()
 
     try:
       if ssc is not None:
@@ -152,6 +161,8 @@ class TFCluster(object):
     finally:
       if armed:
         signal.alarm(0)
+      if timer is not None:
+        timer.cancel()
       self.server.stop()
 
   def tensorboard_url(self):

@@ -357,12 +357,26 @@ class DataFeed(object):
     else:
       names = self.input_tensors
       cols = [batch[t] for t in names]
-    out = []
     use_cuda = torch.cuda.is_available() and (device is None or str(device).startswith("cuda"))
-    for i, c in enumerate(cols):
-      arr = np.asarray(c, dtype=(dtypes[i] if dtypes else None))
-      t = torch.from_numpy(np.ascontiguousarray(arr))
-      if use_cuda:
-        t = t.pin_memory().to(device or "cuda", non_blocking=True)
-      out.append(t)
+    arrs = [np.ascontiguousarray(np.asarray(c, dtype=(dtypes[i] if dtypes else None)))
+            for i, c in enumerate(cols)]
+    if not use_cuda:
+      out = [torch.from_numpy(a) for a in arrs]
+      return out if self.input_tensors is None else dict(zip(names, out))
+    # page-locked staging and the device slots belong to a prefetcher that lives as long as the
+    # feed (re-created only if the batch geometry changes): no cudaHostAlloc / page-lock per batch
+    from .feed import DevicePrefetcher
+    specs = [(tuple(a.shape), torch.from_numpy(a[:0]).dtype) for a in arrs]
+    pf = getattr(self, "_prefetcher", None)
+    if pf is None or self._prefetch_specs != specs:
+      pf = self._prefetcher = DevicePrefetcher(specs, device or "cuda", depth=3)
+      self._prefetch_specs = specs
+    elif getattr(self, "_prefetch_unreleased", False):
+      # the kernels that read the PREVIOUS batch have been enqueued on the current stream by now:
+      # only from this point on may a later copy reuse that batch's device slot
+      pf.release()
+    pf.push_arrays(arrs)
+    slots = pf.pop()
+    self._prefetch_unreleased = True
+    out = list(slots)   # valid until the caller asks for the batch after the next one
     return out if self.input_tensors is None else dict(zip(names, out))

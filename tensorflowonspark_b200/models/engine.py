@@ -85,8 +85,12 @@ class ParamStore(object):
     return self._view(self.aux32, s, self.decay_end)
 
   def state_dict(self):
-    # master is authoritative only for a rank's own shards when world > 1; the bf16 copy and
-    # aux32 are complete everywhere, so checkpoints are assembled by parallel/fused_optim.py.
+    # with world > 1 the fused all-reduce + optimizer kernel keeps the fp32 master current only
+    # for this rank's own shard of every bucket: FusedOptimizer registers assemble(), which pulls
+    # the peers' shards over NVLink before anything is saved or exported
+    assemble = getattr(self, "_assemble", None)
+    if assemble is not None:
+      assemble()
     return {s["name"]: self.m(s).detach().cpu().clone() for s in self.order}
 
   def load_state_dict(self, sd):
@@ -163,6 +167,30 @@ class StatsArena(object):
     ops.count()
 
 
+class RunningArena(object):
+  """The running mean / variance of every batch norm of a trainer in ONE flat fp32 buffer
+  ([mean_0 | var_0 | mean_1 | var_1 ...], each padded to 8 elements): the non-trainable model
+  state is then a single tensor that checkpoints save, exports serve and the parameter server
+  hosts as the tail of its vector (parallel/ps.py)."""
+
+  def __init__(self, device, capacity=1 << 17):
+    self.buf = torch.zeros(capacity, dtype=torch.float32, device=device)
+    self.used = 0
+
+  def take(self, C):
+    C8 = (C + 7) // 8 * 8
+    if self.used + 2 * C8 > self.buf.numel():
+      raise RuntimeError("RunningArena capacity exceeded")
+    mean = self.buf[self.used:self.used + C]
+    var = self.buf[self.used + C8:self.used + C8 + C]
+    var.fill_(1.0)
+    self.used += 2 * C8
+    return mean, var
+
+  def tensor(self):
+    return self.buf[:self.used]
+
+
 class BatchNorm(object):
   """Training-mode batch norm over NHWC bf16 with statistics fused into the producer conv."""
 
@@ -172,10 +200,11 @@ class BatchNorm(object):
     self.sb = store.register(name + ".beta", (C,), False, constant(0.0))
     self.store = store
 
-  def build(self, device, arena=None):
+  def build(self, device, arena=None, running=None):
     """``arena`` (StatsArena): take the (sum, sumsq) accumulators from a per-trainer arena that
     the trainer zeroes once per step; the statistics are then finalised inside the apply kernel
-    (one launch less per batch norm and no clearing pass)."""
+    (one launch less per batch norm and no clearing pass).  ``running`` (RunningArena): place
+    the running statistics in the trainer's flat non-trainable-state buffer."""
     z = lambda: torch.zeros(self.C, dtype=torch.float32, device=device)  # noqa: E731
     self.arena = arena
     if arena is not None:
@@ -183,8 +212,11 @@ class BatchNorm(object):
     else:
       self.sum, self.sumsq = z(), z()
     self.mean, self.invstd, self.scale, self.shift = z(), z(), z(), z()
-    self.running_mean = z()
-    self.running_var = torch.ones(self.C, dtype=torch.float32, device=device)
+    if running is not None:
+      self.running_mean, self.running_var = running.take(self.C)
+    else:
+      self.running_mean = z()
+      self.running_var = torch.ones(self.C, dtype=torch.float32, device=device)
     self.gamma, self.beta = self.store.f32(self.sg), self.store.f32(self.sb)
     self.dgamma, self.dbeta = self.store.g(self.sg), self.store.g(self.sb)
 

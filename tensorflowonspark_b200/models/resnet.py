@@ -46,7 +46,7 @@ class ResNetTrainer(object):
                optimizer="momentum"):
     assert depth in self.CFG, "bottleneck depths: 50/101/152"
     self.device = torch.device(device)
-    self.B, self.image, self.num_classes = batch, image, num_classes
+    self.B, self.image, self.num_classes, self.depth = batch, image, num_classes, depth
     self.training = training
     self.comm = comm
     dev = self.device
@@ -92,7 +92,8 @@ class ResNetTrainer(object):
     # finalisation is folded into the apply kernels (engine.BatchNorm.build)
     self.stats_arena = engine.StatsArena(dev) if (tr and dev.type == "cuda" and os.environ.get(
         "TFOS_BN_FUSED_FINALIZE", "1") != "0") else None
-    self.stem_bn.build(dev, self.stats_arena)
+    self.running = engine.RunningArena(dev)   # all BN running statistics, one flat buffer
+    self.stem_bn.build(dev, self.stats_arena, self.running)
     self.p_stem = igemm.stem_fprop(self.xp, st.w(self.stem_w), self.stem_raw,
                                    stats=self.stem_bn.stats if tr else None)
     if tr:
@@ -122,7 +123,7 @@ class ResNetTrainer(object):
       else:
         b.g_r1 = b.g_a1 = b.g_r2 = b.g_a2 = b.g_r3 = b.g_out = b.g_x = None
       for u in (b.u1, b.u2, b.u3) + ((b.ds,) if b.ds else ()):
-        u.bn.build(dev, self.stats_arena)
+        u.bn.build(dev, self.stats_arena, self.running)
       ident = b.ds is None
       # the block output's ReLU mask (one bit per element, written by bn3's forward): identity
       # blocks fold "mask * dY" into conv1's accumulating dgrad instead of materialising it
@@ -346,6 +347,95 @@ class ResNetTrainer(object):
   def set_lr(self, lr):
     self.optim.set_lr(lr)
 
+  # ------------------------------------------------- checkpoints / serving
+  export_builder = "tensorflowonspark_b200.models.resnet:build_served"
+  export_signatures = {"serving_default": {
+      "inputs": {"image": "image"}, "outputs": {"logits": "logits", "prediction": "prediction"},
+      "input_dtypes": {"image": "uint8"}}}
+
+  @property
+  def export_builder_args(self):
+    return {"depth": self.depth, "image": self.image, "num_classes": self.num_classes}
+
+  def state_dict(self):
+    """Parameters (fp32 masters, assembled across ranks when sharded) + the batch-norm running
+    statistics: everything inference or a resumed run needs."""
+    sd = dict(self.store.state_dict())
+    sd["__running__"] = self.running.tensor().detach().cpu().clone()
+    return sd
+
+  def load_state_dict(self, sd):
+    sd = dict(sd)
+    running = sd.pop("__running__", None)
+    self.store.load_state_dict(sd)
+    if running is not None:
+      self.running.tensor().copy_(running.to(self.device))
+
+
+class ServedResNet(object):
+  """Inference callable behind ``pipeline.TFModel`` / ``TFParallel``: one bf16 replica on the
+  executor's GPU.  ``submit(inputs)`` stages a uint8 NHWC batch in page-locked memory, copies it
+  on the copy stream and enqueues the forward pass + an async read-back of the results;
+  ``collect()`` returns the oldest submitted batch - so the H2D copy of batch i+1 and the host's
+  row handling overlap the kernels of batch i (pipeline._run_model drives it one batch ahead)."""
+
+  def __init__(self, state, depth=50, image=224, num_classes=1000, batch=256, device="cuda:0"):
+    from ..feed import DevicePrefetcher
+    torch.cuda.set_device(torch.device(device))
+    self.net = ResNetTrainer(depth=depth, batch=batch, image=image, num_classes=num_classes,
+                             device=device, training=False)
+    self.net.load_state_dict(state)
+    self.B, self.image, self.V = batch, image, num_classes
+    dev = self.net.device
+    self.feeder = DevicePrefetcher([((batch, image, image, 3), torch.uint8)], dev, depth=2)
+    self.h_logits = [torch.empty(batch, num_classes, dtype=torch.float32).pin_memory()
+                     for _ in range(2)]
+    self.h_pred = [torch.empty(batch, dtype=torch.int64).pin_memory() for _ in range(2)]
+    self.done = [torch.cuda.Event() for _ in range(2)]
+    self._pending = []
+    self._k = 0
+
+  def submit(self, inputs):
+    import numpy as np
+    x = inputs["image"] if isinstance(inputs, dict) else inputs
+    x = np.asarray(x)
+    n = len(x)
+    if n > self.B:
+      raise ValueError("batch of {} rows exceeds the served batch size {}".format(n, self.B))
+    x = x.reshape(n, self.image, self.image, 3)
+    if n < self.B:   # ragged tail: pad (the padded rows' outputs are dropped)
+      x = np.concatenate([x, np.zeros((self.B - n,) + x.shape[1:], dtype=x.dtype)])
+    self.feeder.push_arrays([x])
+    (dx,) = self.feeder.pop()
+    self.net.set_input(dx)
+    self.feeder.release()
+    logits = self.net.forward_only()
+    k = self._k
+    self._k ^= 1
+    self.h_logits[k].copy_(logits[:, :self.V], non_blocking=True)
+    self.h_pred[k].copy_(logits[:, :self.V].argmax(1), non_blocking=True)
+    self.done[k].record(torch.cuda.current_stream(self.net.device))
+    self._pending.append((k, n))
+
+  def collect(self):
+    k, n = self._pending.pop(0)
+    self.done[k].synchronize()
+    return {"logits": self.h_logits[k][:n].numpy().copy(),
+            "prediction": self.h_pred[k][:n].numpy().copy()}
+
+  def pending(self):
+    return len(self._pending)
+
+  def __call__(self, **inputs):
+    self.submit(inputs)
+    return self.collect()
+
+
+def build_served(state, depth=50, image=224, num_classes=1000, batch=None, **_):
+  """Export builder (utils/checkpoint.py): rebuilds the replica on the executor's GPU."""
+  batch = int(batch or os.environ.get("TFOS_SERVE_BATCH", "256"))
+  return ServedResNet(state, depth=depth, image=image, num_classes=num_classes, batch=batch)
+
 
 class CifarResNetTrainer(object):
   """ResNet-20/32/56 for 32x32 inputs (basic blocks, 16/32/64 channels) - the network the
@@ -383,7 +473,8 @@ class CifarResNetTrainer(object):
     self.labels = torch.zeros(B, dtype=torch.int32, device=dev)
     self.stem_raw, self.stem_act = _buf((B, 32, 32, 16), dev), _buf((B, 32, 32, 16), dev)
     self.g_stem_raw = _buf((B, 32, 32, 16), dev)
-    self.stem.bn.build(dev)
+    self.running = engine.RunningArena(dev)
+    self.stem.bn.build(dev, None, self.running)
     gx = _buf((B, 32, 32, 16), dev)
     self.g_stem_act = gx
     self.stem.conv.build(self.x8, self.stem_raw, self.g_stem_raw, None, stats=self.stem.bn.stats,
@@ -398,7 +489,7 @@ class CifarResNetTrainer(object):
       b.g_out = _buf(b.out.shape, dev) if b.ds is not None else gx
       b.g_x = gx
       for u in (b.u1, b.u2) + ((b.ds,) if b.ds else ()):
-        u.bn.build(dev)
+        u.bn.build(dev, None, self.running)
       ident = b.ds is None
       b.u1.conv.build(x, b.r1, b.g_r1, b.g_x, stats=b.u1.bn.stats, dx_accumulate=ident)
       b.u2.conv.build(b.a1, b.r2, b.g_r2, b.g_a1, stats=b.u2.bn.stats)
@@ -420,6 +511,8 @@ class CifarResNetTrainer(object):
     self.mean, self.std = [0.4914, 0.4822, 0.4465], [0.2470, 0.2435, 0.2616]
 
   synthetic_batch = ResNetTrainer.synthetic_batch
+  state_dict = ResNetTrainer.state_dict
+  load_state_dict = ResNetTrainer.load_state_dict
   set_input = ResNetTrainer.set_input
   capture = ResNetTrainer.capture
   train_step = ResNetTrainer.train_step

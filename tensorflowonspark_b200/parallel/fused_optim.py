@@ -34,8 +34,17 @@ class FusedOptimizer(object):
     self.rank = comm.rank if comm is not None else 0
     self.hyper = torch.tensor([lr, momentum, weight_decay, 1.0 / self.world, beta1, beta2, eps, 0.0],
                               dtype=torch.float32, device=dev)
-    self.state1 = torch.zeros_like(store.master) if self.opt != 0 else None
-    self.state2 = torch.zeros_like(store.master) if self.opt == 2 else None
+    # with peers, the optimizer state lives in symmetric memory like the master copy: a rank only
+    # ever updates its own shard of each bucket, so whoever saves a checkpoint pulls the other
+    # shards over NVLink (assemble())
+    def _state(name):
+      if comm is not None and self.world > 1:
+        t = comm.alloc(name, store.total, torch.float32)
+        t.zero_()
+        return t
+      return torch.zeros_like(store.master)
+    self.state1 = _state("state1") if self.opt != 0 else None
+    self.state2 = _state("state2") if self.opt == 2 else None
     self.step_count = 0
     self.grid = grid or (148 if self.world == 1 else 64)
     n = store.total
@@ -72,6 +81,7 @@ class FusedOptimizer(object):
     for i, (_, _, tag) in enumerate(self.buckets):
       self._by_tag.setdefault(tag, []).append(i)
     self._launched = set()
+    store._assemble = self.assemble   # ParamStore.state_dict() must see every rank's shards
     self.overlap = len(self.buckets) > 1 and dev.type == "cuda"
     if self.overlap:
       self.comm_stream = torch.cuda.Stream(device=dev)
@@ -159,7 +169,46 @@ class FusedOptimizer(object):
     for i in todo:
       ops.K.allreduce_opt(self._args[i])
 
+  # ------------------------------------------------------ sharded state
+  def shard_bounds(self, bucket, rank):
+    """[lo, hi) of ``rank``'s shard of bucket ``bucket`` - the same arithmetic as
+    allreduce_opt_kernel (csrc/optim_comm.cu): ceil(n / world) rounded up to 8 elements."""
+    b, e, _ = self.buckets[bucket]
+    n = e - b
+    chunk = ((n + self.world - 1) // self.world + 7) // 8 * 8
+    return b + min(n, chunk * rank), b + min(n, chunk * (rank + 1))
+
+  def assemble(self):
+    """Make THIS rank's fp32 master and optimizer state complete.
+
+    With world > 1 the fused kernel updates master/state only for the rank's own shard of every
+    bucket; the rest of the local copy is stale.  This pulls every peer's shards out of the
+    peers' symmetric buffers (plain device copies over NVLink on the current stream).  It is not
+    a collective: only the saving rank needs to call it.  It is consistent as long as it is
+    stream-ordered between two of this rank's steps - a peer cannot finish its next update
+    before this rank has contributed its gradients (the kernel's entry barrier)."""
+    if self.world == 1 or self.comm is None:
+      return
+    C = ops.C()
+    n = self.store.total
+    bufs = [("master", self.store.master)]
+    if self.state1 is not None:
+      bufs.append(("state1", self.state1))
+    if self.state2 is not None:
+      bufs.append(("state2", self.state2))
+    for name, local in bufs:
+      ptrs = self.comm.peer_ptrs(name)
+      for r in range(self.world):
+        if r == self.rank:
+          continue
+        remote = C.tensor_from_ptr(ptrs[r], [n], "f32")
+        for i in range(len(self.buckets)):
+          lo, hi = self.shard_bounds(i, r)
+          if hi > lo:
+            local[lo:hi].copy_(remote[lo:hi])
+
   def state_dict(self):
+    self.assemble()
     sd = {"step": self.step_count}
     if self.state1 is not None:
       sd["state1"] = self.state1.detach().cpu()

@@ -259,17 +259,53 @@ _model_cache = {"key": None, "model": None, "sig": None}
 
 def _load_cached(args):
   from .utils import checkpoint
-  key = (args.export_dir, args.tag_set, args.signature_def_key)
+  export_dir = getattr(args, "export_dir", None)
+  model_dir = getattr(args, "model_dir", None)
+  key = (export_dir, model_dir, args.tag_set, args.signature_def_key)
   if _model_cache["key"] != key:
-    assert args.export_dir, "TFModel needs export_dir"
-    model, sig = checkpoint.load_model(args.export_dir, args.tag_set)
+    assert export_dir or model_dir, "TFModel needs export_dir (or a model_dir with checkpoints)"
+    if export_dir:
+      model, sig = checkpoint.load_model(export_dir, args.tag_set)
+    else:  # reference pipeline.py:549-555: no export -> the latest checkpoint of model_dir
+      model, sig = checkpoint.load_model_dir(model_dir)
     _model_cache.update(key=key, model=model, sig=sig)
-    logger.info("loaded model from %s", args.export_dir)
+    logger.info("loaded model from %s", export_dir or model_dir)
   return _model_cache["model"], _model_cache["sig"]
 
 
+def _column_to_array(values, dtype=None, shape=None):
+  """One batch column (a list of row values) -> ndarray [n, ...] with no per-element Python
+  work where the values allow it: binary cells (bytes / bytearray / memoryview - how a DataFrame
+  carries image tensors; recognised by an ``input_dtypes`` entry in the signature) are viewed
+  with ``np.frombuffer`` and copied row-wise into one buffer,
+  ndarray cells are stacked; only genuine Python lists go through ``np.asarray``."""
+  import numpy as np
+  v0 = values[0]
+  if dtype is not None and isinstance(v0, (bytes, bytearray, memoryview)):
+    # the signature declares a dtype for this input: binary cells are raw tensor bytes
+    dt = np.dtype(dtype)
+    out = np.empty((len(values), len(v0) // dt.itemsize), dtype=dt)
+    for i, b in enumerate(values):
+      out[i] = np.frombuffer(b, dtype=dt)
+    arr = out
+  elif isinstance(v0, np.ndarray):
+    arr = np.stack(values)
+    if dtype is not None and arr.dtype != np.dtype(dtype):
+      arr = arr.astype(dtype)
+  else:
+    arr = np.asarray(values, dtype=dtype)
+  if shape:  # Spark only carries flat arrays: restore the signature's shape
+    arr = arr.reshape([-1] + [int(d) for d in shape[1:]])
+  return arr
+
+
 def _run_model(iterator, args, tf_args):
-  """mapPartitions body of TFModel.transform: batches rows, runs the cached model, emits rows."""
+  """mapPartitions body of TFModel.transform (reference pipeline.py:618-645 / the Scala
+  TFModel.scala:245-292 batch loop): batches rows column-wise, runs the cached model, emits rows.
+
+  A served model that offers ``submit(inputs)`` / ``collect()`` (the GPU replicas in models/) is
+  driven one batch ahead: batch i+1 is staged in pinned memory and copied on the copy stream
+  while the kernels of batch i run and its results travel back."""
   import numpy as np
   single_node_env(tf_args)
   model, sig = _load_cached(args)
@@ -278,16 +314,9 @@ def _run_model(iterator, args, tf_args):
   in_names = [t for _, t in sorted(args.input_mapping.items())]
   out_names = [t for t, _ in sorted(args.output_mapping.items())]
   shapes = signature.get("input_shapes", {})
-  results = []
-  for tensors in yield_batch(iterator, args.batch_size, len(in_names)):
-    inputs = {}
-    for name, col in zip(in_names, tensors):
-      arr = np.asarray(col)
-      shp = shapes.get(name)
-      if shp:  # Spark only carries flat arrays: restore the signature's shape
-        arr = arr.reshape([-1] + [int(d) for d in shp[1:]])
-      inputs[name] = arr
-    outputs = model(**inputs) if callable(model) else _apply_state(model, inputs)
+  dtypes = signature.get("input_dtypes", {})
+
+  def emit(outputs, n):
     if not isinstance(outputs, dict):
       outputs = {out_names[0]: outputs}
     cols = []
@@ -300,11 +329,29 @@ def _run_model(iterator, args, tf_args):
         o = (o.float() if o.dtype.is_floating_point and o.element_size() < 4 else o).numpy()
       else:
         o = np.asarray(o)
-      assert len(o) == len(tensors[0]), "output '{}' has {} rows, expected {}".format(
-          t, len(o), len(tensors[0]))
-      cols.append(o.tolist())
-    results.extend(zip(*cols))
-  return results
+      assert len(o) == n, "output '{}' has {} rows, expected {}".format(t, len(o), n)
+      cols.append(o.tolist())   # Row cells must be plain Python values
+    return zip(*cols)
+
+  pipelined = hasattr(model, "submit") and hasattr(model, "collect")
+  waiting = []                  # row counts of the batches submitted but not yet collected
+  for tensors in yield_batch(iterator, args.batch_size, len(in_names)):
+    inputs = {name: _column_to_array(col, dtypes.get(name), shapes.get(name))
+              for name, col in zip(in_names, tensors)}
+    n = len(tensors[0])
+    if pipelined:
+      model.submit(inputs)
+      waiting.append(n)
+      if len(waiting) > 1:
+        for row in emit(model.collect(), waiting.pop(0)):
+          yield row
+    else:
+      outputs = model(**inputs) if callable(model) else _apply_state(model, inputs)
+      for row in emit(outputs, n):
+        yield row
+  while waiting:
+    for row in emit(model.collect(), waiting.pop(0)):
+      yield row
 
 
 def _apply_state(state, inputs):

@@ -45,11 +45,18 @@ def _atomic_torch_save(obj, path):
     raise
 
 
-def save(model_dir, step, state, keep=5):
-  """Write ``state`` (any picklable / tensor dict) as checkpoint ``step``; prune old ones."""
+def save(model_dir, step, state, keep=5, model=None, signatures=None):
+  """Write ``state`` (any picklable / tensor dict) as checkpoint ``step``; prune old ones.
+
+  ``model`` (optional): the object the state came from.  Its ``export_builder`` is recorded in
+  ``model_dir/signature.json`` so that the newest checkpoint can be *served* without an export
+  (``load_model_dir``; the reference's TFModel falls back to ``tf.train.latest_checkpoint(
+  model_dir)`` when no ``export_dir`` is given, pipeline.py:549-555)."""
   model_dir = _local(model_dir)
   path = os.path.join(model_dir, "ckpt-{:08d}.pt".format(int(step)))
   _atomic_torch_save({"step": int(step), "state": state}, path)
+  if model is not None and getattr(model, "export_builder", None):
+    _write_signature(model_dir, model, "serve", signatures)
   tmp = os.path.join(model_dir, "." + INDEX + ".tmp")
   with open(tmp, "w") as f:
     json.dump({"latest": os.path.basename(path), "step": int(step)}, f)
@@ -101,6 +108,21 @@ def _state_of(model):
   raise TypeError("cannot export object of type {}".format(type(model)))
 
 
+def _write_signature(directory, model, tag_set, signatures, builder=None):
+  sig = {
+      "tag_set": tag_set if isinstance(tag_set, (list, tuple)) else str(tag_set).split(","),
+      "signatures": signatures or getattr(model, "export_signatures", None)
+      or {"serving_default": {"inputs": {}, "outputs": {}}},
+      "builder": builder or getattr(model, "export_builder", None),
+      "builder_args": getattr(model, "export_builder_args", {}),
+  }
+  tmp = os.path.join(directory, ".signature.tmp")
+  with open(tmp, "w") as f:
+    json.dump(sig, f, indent=1)
+  os.replace(tmp, os.path.join(directory, "signature.json"))
+  return sig
+
+
 def export_model(model, export_dir, tag_set="serve", signatures=None, builder=None):
   """Write the inference artefact.
 
@@ -116,23 +138,42 @@ def export_model(model, export_dir, tag_set="serve", signatures=None, builder=No
   export_dir = _local(export_dir)
   os.makedirs(export_dir, exist_ok=True)
   _atomic_torch_save(_state_of(model), os.path.join(export_dir, "weights.pt"))
-  sig = {
-      "tag_set": tag_set if isinstance(tag_set, (list, tuple)) else str(tag_set).split(","),
-      "signatures": signatures or {"serving_default": {"inputs": {}, "outputs": {}}},
-      "builder": builder or getattr(model, "export_builder", None),
-      "builder_args": getattr(model, "export_builder_args", {}),
-  }
-  tmp = os.path.join(export_dir, ".signature.tmp")
-  with open(tmp, "w") as f:
-    json.dump(sig, f, indent=1)
-  os.replace(tmp, os.path.join(export_dir, "signature.json"))
+  _write_signature(export_dir, model, tag_set, signatures, builder)
   logger.info("exported model to %s", export_dir)
   return export_dir
 
 
+def _build(sig, state):
+  import importlib
+  if sig.get("builder"):
+    mod, fn = sig["builder"].split(":")
+    return getattr(importlib.import_module(mod), fn)(state, **sig.get("builder_args", {}))
+  return state
+
+
+def load_model_dir(model_dir, map_location="cpu"):
+  """(callable, signature_json) from the NEWEST CHECKPOINT of a training ``model_dir`` - the
+  inference fallback when nothing was exported (reference pipeline.py:549-555).  Needs the
+  ``signature.json`` that ``save(..., model=...)`` writes next to the checkpoints."""
+  model_dir = _local(model_dir)
+  sig_path = os.path.join(model_dir, "signature.json")
+  latest = latest_checkpoint(model_dir)
+  if latest is None:
+    raise IOError("no checkpoint found in model_dir {}".format(model_dir))
+  if not os.path.exists(sig_path):
+    raise IOError("{} has checkpoints but no signature.json: save them with "
+                  "checkpoint.save(..., model=<model>) to make them servable".format(model_dir))
+  with open(sig_path) as f:
+    sig = json.load(f)
+  _, state = load(latest, map_location)
+  if isinstance(state, dict) and "model" in state and "optimizer" in state:
+    state = state["model"]      # a training checkpoint: only the parameters are served
+  logger.info("serving checkpoint %s", latest)
+  return _build(sig, state), sig
+
+
 def load_model(export_dir, tag_set=None, map_location="cpu"):
   """(callable_or_state_dict, signature_json) from an exported artefact."""
-  import importlib
   import torch
   export_dir = _local(export_dir)
   with open(os.path.join(export_dir, "signature.json")) as f:
@@ -144,8 +185,4 @@ def load_model(export_dir, tag_set=None, map_location="cpu"):
                                                                        want))
   state = torch.load(os.path.join(export_dir, "weights.pt"), map_location=map_location,
                      weights_only=False)
-  if sig.get("builder"):
-    mod, fn = sig["builder"].split(":")
-    model = getattr(importlib.import_module(mod), fn)(state, **sig.get("builder_args", {}))
-    return model, sig
-  return state, sig
+  return _build(sig, state), sig

@@ -135,3 +135,24 @@ def test_second_node_task_on_live_executor_is_rejected():
     TFManager._owned[0].shutdown()
     TFSparkNode.TFSparkNode.mgr = None
     os.remove("executor_id")
+
+
+def test_gpu_index_is_per_host_position_in_the_cluster_spec():
+  """Several nodes on one host must take disjoint GPUs: the slot handed to gpu_info is the node's
+  position among the nodes OF ITS HOST in the (mocked) cluster spec, not the executor id
+  (reference tests/test_TFSparkNode.py:89-106: worker:1 of 1.1.1.1 -> index 2)."""
+  spec = {"chief": ["1.1.1.1:2222"], "worker": ["1.1.1.1:2223", "1.1.1.1:2224", "2.2.2.2:2222"]}
+  calls = []
+
+  def fake_get_gpus(n, index, format=None):  # noqa: A002
+    calls.append((n, index, format))
+    return ["0"]
+
+  with mock.patch.object(gpu_info, "is_gpu_available", return_value=True), \
+       mock.patch.object(gpu_info, "get_gpus", side_effect=fake_get_gpus), \
+       mock.patch.object(TFSparkNode, "_has_spark_resource_api", return_value=False), \
+       mock.patch.dict(os.environ, {}, clear=False):
+    os.environ.pop("SPARK_EXECUTOR_POD_IP", None)
+    for job, idx, want in (("chief", 0, 0), ("worker", 0, 1), ("worker", 1, 2), ("worker", 2, 0)):
+      TFSparkNode._get_gpus({"num_gpus": 1}, 7, cluster_spec=spec, job_name=job, task_index=idx)
+      assert calls[-1] == (1, want, gpu_info.AS_LIST), (job, idx, calls[-1])

@@ -1,0 +1,68 @@
+"""Whole example programs on the 2-executor CPU engine - the plumbing bar of BASELINE.json
+config #1 ("MNIST InputMode.SPARK sync SGD local[2] on CPU") and of the other MNIST drivers
+(reference examples/mnist/keras/{mnist_spark,mnist_tf_ds}.py, estimator/mnist_pipeline.py)."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(args, timeout=420, env=None):
+  e = dict(os.environ, CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="2")
+  e.update(env or {})
+  p = subprocess.run([sys.executable] + args, capture_output=True, text=True, timeout=timeout,
+                     cwd=ROOT, env=e)
+  assert p.returncode == 0, (p.stdout[-3000:], p.stderr[-3000:])
+  return p.stdout + p.stderr
+
+
+@pytest.fixture(scope="module")
+def mnist(tmp_path_factory):
+  d = str(tmp_path_factory.mktemp("mnist"))
+  _run(["examples/mnist/mnist_data_setup.py", "--output", d + "/data", "--train_size", "2048",
+        "--test_size", "256", "--num_partitions", "4"])
+  return d
+
+
+def test_baseline_config_1_mnist_inputmode_spark_sync_sgd_local2(mnist):
+  out = _run(["examples/mnist/mnist_spark.py", "--cluster_size", "2", "--images_labels",
+              mnist + "/data/csv/train", "--epochs", "2", "--batch_size", "32",
+              "--learning_rate", "0.05", "--export_dir", mnist + "/export_spark",
+              "--model_dir", mnist + "/model_spark"])
+  assert "gloo, world 2" in out                       # two CPU workers in one process group
+  assert os.path.exists(mnist + "/export_spark/weights.pt")
+  losses = [float(x) for x in re.findall(r"loss ([\d.]+)", out)]
+  assert not losses or losses[-1] < 2.4               # (fewer than 100 steps print nothing)
+  inf = _run(["examples/mnist/mnist_inference.py", "--cluster_size", "2", "--images_labels",
+              mnist + "/data/tfr/test", "--export_dir", mnist + "/export_spark", "--output",
+              mnist + "/pred_spark"])
+  assert float(re.search(r"accuracy: ([\d.]+)", inf).group(1)) > 0.5
+
+
+def test_mnist_tf_ds_streaming_tfrecord_pipeline(mnist):
+  out = _run(["examples/mnist/mnist_tf_ds.py", "--cluster_size", "2", "--images_labels",
+              mnist + "/data/tfr/train/part-*", "--epochs", "2", "--batch_size", "32",
+              "--num_examples", "2048", "--buffer_size", "512", "--learning_rate", "0.05",
+              "--model_dir", mnist + "/model_ds", "--export_dir", mnist + "/export_ds"])
+  assert out.count("saved weights to") == 2           # one weights checkpoint per epoch
+  assert os.path.exists(mnist + "/export_ds/signature.json")
+  assert os.path.exists(mnist + "/model_ds/signature.json")   # checkpoints are servable
+
+
+def test_estimator_pipeline_train_then_serve_newest_checkpoint(mnist):
+  _run(["examples/mnist/estimator/mnist_pipeline.py", "--cluster_size", "2", "--images_labels",
+        mnist + "/data/csv/train", "--epochs", "2", "--batch_size", "32", "--learning_rate",
+        "0.05", "--model_dir", mnist + "/model_est", "--export_dir", mnist + "/export_est"])
+  assert os.path.exists(mnist + "/export_est/weights.pt")
+  # inference from the export, then with NO export: TFModel falls back to model_dir's newest
+  # checkpoint (reference pipeline.py:549-555)
+  for export in (mnist + "/export_est", mnist + "/no_such_export"):
+    out = _run(["examples/mnist/estimator/mnist_pipeline.py", "--mode", "inference", "--format",
+                "tfr", "--cluster_size", "2", "--images_labels", mnist + "/data/tfr/test",
+                "--model_dir", mnist + "/model_est", "--export_dir", export, "--output",
+                mnist + "/pred_est"])
+    assert float(re.search(r"inference accuracy: ([\d.]+)", out).group(1)) > 0.5

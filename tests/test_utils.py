@@ -117,3 +117,20 @@ def test_usable_cpus_and_thread_limit(monkeypatch):
   assert 1 <= t <= 8 and os.environ["OMP_NUM_THREADS"] == str(t)
   monkeypatch.setenv("OMP_NUM_THREADS", "3")
   assert util.limit_intra_op_threads(1) == 3       # an explicit setting wins
+
+
+def test_fused_optimizer_shards_partition_every_bucket():
+  """The host-side shard arithmetic used to assemble checkpoints must mirror the kernel's:
+  shards of a bucket are disjoint, ordered, 8-aligned and cover [begin, end) exactly."""
+  from tensorflowonspark_b200.parallel.fused_optim import FusedOptimizer
+  for world in (1, 2, 3, 8):
+    opt = FusedOptimizer.__new__(FusedOptimizer)
+    opt.world = world
+    opt.buckets = [(0, 1000, None), (1000, 25_557_040, None), (25_557_040, 25_557_048, None)]
+    for i, (b, e, _) in enumerate(opt.buckets):
+      pos = b
+      for r in range(world):
+        lo, hi = opt.shard_bounds(i, r)
+        assert lo == pos and lo <= hi <= e and (lo - b) % 8 == 0
+        pos = hi
+      assert pos == e

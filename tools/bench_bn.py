@@ -45,9 +45,11 @@ def main():
         ("bwd_reduce m2", lambda: K.bn_bwd_reduce(dy, x, None, mean, invstd, dg, db, 2, sc, sh), 2),
         ("bwd_reduce m1", lambda: K.bn_bwd_reduce(dy, x, y, mean, invstd, dg, db, 1, None, None), 3),
         ("bwd_apply m2", lambda: K.bn_bwd_apply(dy, x, None, gamma, mean, invstd, dg, db, out, None, 2, sc, sh), 3),
-        ("bwd_apply m1+dres", lambda: K.bn_bwd_apply(dy, x, y, gamma, mean, invstd, dg, db, out, res, 1, None, None), 5),
+        ("bwd_apply m1+dres",
+         lambda: K.bn_bwd_apply(dy, x, y, gamma, mean, invstd, dg, db, out, res, 1, None, None), 5),
         ("bwd_reduce m3", lambda: K.bn_bwd_reduce(dy, x, bits, mean, invstd, dg, db, 3, None, None), 2.0625),
-        ("bwd_apply m3+dres", lambda: K.bn_bwd_apply(dy, x, bits, gamma, mean, invstd, dg, db, out, res, 3, None, None), 4.0625),
+        ("bwd_apply m3+dres",
+         lambda: K.bn_bwd_apply(dy, x, bits, gamma, mean, invstd, dg, db, out, res, 3, None, None), 4.0625),
     ]
     for name, fn, passes in cases:
       us = timeit(fn)

@@ -44,5 +44,6 @@ w = net.store.weights.float()
 ref = w.clone(); dist.broadcast(ref, 0)
 diff = float((w - ref).abs().max())
 m = net.store.master.clone()
-print("rank {} {}: {:.1f} ms/step (one rank sleeps 50 ms) | max |bf16 weights - rank0's| = {:.3e}".format(rank, which, dt, diff), flush=True)
+print("rank {} {}: {:.1f} ms/step (one rank sleeps 50 ms) | max |bf16 weights - rank0's| = {:.3e}".format(
+    rank, which, dt, diff), flush=True)
 dist.barrier(); dist.destroy_process_group()
