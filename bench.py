@@ -39,6 +39,12 @@ def parse_args():
   p.add_argument("--impl", default="ours", choices=["ours", "reference", "nccl-cudnn"],
                  help="ours | reference (the unmodified reference: unavailable on this image) | "
                       "nccl-cudnn (stock torchvision + cuDNN + DDP/NCCL comparator, same contract)")
+  p.add_argument("--config", default="resnet50", choices=["resnet50", "ps", "unet", "infer"],
+                 help="BASELINE.json configuration: resnet50 = the headline (sync data-parallel "
+                      "training); ps = async parameter server (1 ps + N-1 workers); unet = U-Net "
+                      "fed through InputMode.SPARK DataFeed; infer = ResNet-50 inference through "
+                      "pipeline.TFModel.  The secondary ones launch their own executors: run "
+                      "them with plain `python bench.py --config X --gpus N`.")
   p.add_argument("--batch", type=int, default=int(os.environ.get("TFOS_BENCH_BATCH", "256")),
                  help="per-GPU batch")
   p.add_argument("--image", type=int, default=224)
@@ -129,6 +135,29 @@ def reference_arm(args):
   return 0
 
 
+def secondary_config(args):
+  """The other BASELINE.json configurations (bench/*.py), same JSON contract.  They start their
+  own executor processes (one per GPU) through TFCluster / TFParallel / TFModel, so under
+  torchrun only rank 0 drives them."""
+  if int(os.environ.get("RANK", "0")) != 0:
+    return 0
+  for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+    os.environ.pop(k, None)    # the executors form their own cluster
+  sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "bench"))
+  if args.config == "ps":
+    import ps_resnet50
+    rec = ps_resnet50.run(max(2, args.gpus), args.batch, args.steps, args.warmup)
+  elif args.config == "infer":
+    import inference_resnet50
+    rec = inference_resnet50.run(args.gpus, args.batch, max(args.steps, 8))
+  else:
+    import unet_datafeed
+    rec = unet_datafeed.run(args.gpus, steps=args.steps)
+  rec["impl"] = "ours"
+  print(json.dumps(rec))
+  return 0
+
+
 class Watchdog(object):
   """A benchmark must never hang its caller.  If no result was printed after ``seconds``
   (TFOS_BENCH_WATCHDOG_S, default 300; a 1-GPU run takes about a minute), dump every thread's
@@ -166,6 +195,8 @@ def main():
   args = parse_args()
   if args.impl == "reference":
     return reference_arm(args)
+  if args.config != "resnet50":
+    return secondary_config(args)
   if args.impl == "nccl-cudnn":
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "baseline"))
     import nccl_cudnn_resnet50
@@ -361,7 +392,7 @@ def supervised_main():
   process under a timeout and retried once: a stalled box must cost one retry, not the headline
   number.  torchrun ranks (WORLD_SIZE set) and the reference arm run directly."""
   args = parse_args()
-  if (args.impl != "ours" or args.profile_step or os.environ.get("TFOS_BENCH_CHILD") == "1"
+  if (args.impl != "ours" or args.config != "resnet50" or args.profile_step or os.environ.get("TFOS_BENCH_CHILD") == "1"
       or int(os.environ.get("WORLD_SIZE", "1")) > 1 or "RANK" in os.environ
       or os.environ.get("TFOS_BENCH_SUPERVISE", "1") == "0"):
     return main()

@@ -13,6 +13,7 @@
 #include "igemm.h"
 #include "ops.h"
 #include "tfrecord.h"
+#include "vmm.h"
 
 namespace py = pybind11;
 using torch::Tensor;
@@ -444,6 +445,7 @@ void allreduce_opt(const py::dict& d) {
   }
   a.grads_mc = reinterpret_cast<const float*>(geti<uint64_t>(d, "grads_mc", 0));
   a.weights_mc = reinterpret_cast<__nv_bfloat16*>(geti<uint64_t>(d, "weights_mc", 0));
+  a.aux32_mc = reinterpret_cast<float*>(geti<uint64_t>(d, "aux32_mc", 0));
   const int opt = geti<int>(d, "opt", 0);
   const int grid = geti<int>(d, "grid", 32);
   check(tfos::allreduce_opt(a, opt, grid, cur_stream()), "allreduce_opt");
@@ -491,6 +493,61 @@ void ps_pull(uint64_t w_ps, c10::optional<Tensor> w_local, c10::optional<Tensor>
         "ps_pull");
 }
 
+template <typename T>
+T* ptr_of(const py::dict& d, const char* k) {
+  return reinterpret_cast<T*>(geti<uint64_t>(d, k, 0));
+}
+void ps_apply(const py::dict& d) {
+  tfos::PsApplyArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.master = ptr_of<float>(d, "master");
+  a.state1 = ptr_of<float>(d, "state1");
+  a.state2 = ptr_of<float>(d, "state2");
+  a.wbf16 = ptr_of<__nv_bfloat16>(d, "wbf16");
+  a.slot = ptr_of<const float>(d, "slot");
+  a.hyper = ptr_of<const float>(d, "hyper");
+  a.n = geti<long long>(d, "n", 0);
+  a.lo = geti<long long>(d, "lo", 0);
+  a.decay_end = geti<long long>(d, "decay_end", 0);
+  a.ema_begin = geti<long long>(d, "ema_begin", 0);
+  a.applied_flag = ptr_of<uint32_t>(d, "applied_flag");
+  a.seq = geti<uint32_t>(d, "seq", 0);
+  a.block_counter = ptr_of<uint32_t>(d, "block_counter");
+  check(tfos::ps_apply(a, geti<int>(d, "opt", 0), cur_stream()), "ps_apply");
+}
+void ps_push_slot(const py::dict& d) {
+  tfos::PsPushArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.slot = ptr_of<float>(d, "slot");
+  a.grads = ptr_of<const float>(d, "grads");
+  a.running = ptr_of<const float>(d, "running");
+  a.running_pulled = ptr_of<const float>(d, "running_pulled");
+  a.n = geti<long long>(d, "n", 0);
+  a.lo = geti<long long>(d, "lo", 0);
+  a.total = geti<long long>(d, "total", 0);
+  a.applied_flag = ptr_of<const uint32_t>(d, "applied_flag");
+  a.need_applied = geti<uint32_t>(d, "need_applied", 0);
+  a.ready_flag = ptr_of<uint32_t>(d, "ready_flag");
+  a.seq = geti<uint32_t>(d, "seq", 0);
+  a.block_counter = ptr_of<uint32_t>(d, "block_counter");
+  check(tfos::ps_push_slot(a, geti<int>(d, "grid", 64), cur_stream()), "ps_push_slot");
+}
+void ps_pull_model(const py::dict& d) {
+  tfos::PsPullArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.wbf16 = ptr_of<const __nv_bfloat16>(d, "wbf16");
+  a.master = ptr_of<const float>(d, "master");
+  a.weights = ptr_of<__nv_bfloat16>(d, "weights");
+  a.aux32 = ptr_of<float>(d, "aux32");
+  a.running = ptr_of<float>(d, "running");
+  a.running_pulled = ptr_of<float>(d, "running_pulled");
+  a.n = geti<long long>(d, "n", 0);
+  a.lo = geti<long long>(d, "lo", 0);
+  a.total = geti<long long>(d, "total", 0);
+  a.decay_end = geti<long long>(d, "decay_end", 0);
+  check(tfos::ps_pull_model(a, geti<int>(d, "grid", 64), cur_stream()), "ps_pull_model");
+}
+
 // ------------------------------------------------ symmetric memory (CUDA IPC)
 // A symmetric buffer is a plain cudaMalloc allocation whose IPC handle is
 // exchanged through the reservation/node_meta channel; peers map it with
@@ -523,8 +580,14 @@ Tensor tensor_from_ptr(uint64_t ptr, std::vector<int64_t> sizes, const std::stri
   else TORCH_CHECK(false, "unknown dtype ", dtype);
   int dev = 0;
   cudaGetDevice(&dev);
-  return torch::from_blob(reinterpret_cast<void*>(ptr), sizes,
-                          torch::TensorOptions().dtype(dt).device(torch::kCUDA, dev));
+  // target_device: the pointer may be a peer's memory mapped into this process (CUDA IPC or an
+  // imported cuMem allocation, whose pointer attributes name the OWNING device); it is addressed
+  // from the current device, so the tensor is declared there and torch's ownership check skipped
+  const c10::Device here(torch::kCUDA, static_cast<c10::DeviceIndex>(dev));
+  return at::for_blob(reinterpret_cast<void*>(ptr), sizes)
+      .options(torch::TensorOptions().dtype(dt).device(here))
+      .target_device(here)
+      .make_tensor();
 }
 
 }  // namespace
@@ -565,6 +628,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("ps_push_dense", &ps_push_dense);
   m.def("ps_push_sparse", &ps_push_sparse);
   m.def("ps_pull", &ps_pull);
+  m.def("ps_apply", &ps_apply);
+  m.def("ps_push_slot", &ps_push_slot);
+  m.def("ps_pull_model", &ps_pull_model);
   m.def("symm_alloc", &symm_alloc);
   m.def("symm_open", &symm_open);
   m.def("symm_close", &symm_close);
@@ -573,4 +639,5 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("num_sms", &num_sms);
   tfos::bind_feed(m);
   tfos::bind_tfrecord(m);
+  tfos::bind_vmm(m);
 }

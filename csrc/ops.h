@@ -89,6 +89,7 @@ struct AllreduceOptArgs {
   long long aux_begin;                 //   (BN scale/offset, biases); may be null
   const float* grads_mc;               // NVLS multicast views (optional)
   __nv_bfloat16* weights_mc;
+  float* aux32_mc;
   uint32_t* epoch;          // local, one word per slot
   uint32_t* block_counter;  // local, one word per slot
 };
@@ -109,6 +110,46 @@ cudaError_t ps_push_dense(float* w_ps, const float* g, long long n, const float*
 cudaError_t ps_push_sparse(float* w_ps, const float* g_rows, const int* idx, int nrows, int width,
                            const float* hyper, cudaStream_t s);
 cudaError_t ps_pull(const float* w_ps, float* w_local, void* w_bf16, long long n, cudaStream_t s);
+
+// parameter server with resident optimizer state ("slot mode", parallel/ps.py)
+struct PsApplyArgs {          // server side, all pointers local to the PS GPU
+  float* master;              // [n] fp32 parameters of this server's slice (+ non-trainable tail)
+  float* state1;              // momentum / Adam m (may be null for SGD)
+  float* state2;              // Adam v
+  __nv_bfloat16* wbf16;       // [n] bf16 serving copy that workers pull
+  const float* slot;          // [n] one worker's gradient slot
+  const float* hyper;         // lr, momentum, wd, grad_scale, beta1, beta2, eps, step
+  long long n, lo;            // slice length and its global offset
+  long long decay_end;        // global: elements below receive weight decay
+  long long ema_begin;        // global: elements from here on are running statistics
+  uint32_t* applied_flag;     // this slot's "applied" word
+  uint32_t seq;
+  uint32_t* block_counter;
+};
+struct PsPushArgs {           // worker side
+  float* slot;                // peer-mapped: this worker's slot on the PS GPU
+  const float* grads;         // local fp32 gradients [total]
+  const float* running;       // local running statistics after the step [n_running]
+  const float* running_pulled;  // their values as pulled before the step
+  long long n, lo, total;     // slice length / global offset; total = number of parameters
+  const uint32_t* applied_flag;  // peer-mapped
+  uint32_t need_applied;
+  uint32_t* ready_flag;       // peer-mapped
+  uint32_t seq;
+  uint32_t* block_counter;    // local
+};
+struct PsPullArgs {           // worker side
+  const __nv_bfloat16* wbf16;   // peer-mapped bf16 serving copy of the slice
+  const float* master;        // peer-mapped fp32 slice
+  __nv_bfloat16* weights;     // local bf16 weights [total]
+  float* aux32;               // local fp32 replica of [decay_end, total)
+  float* running;             // local running statistics
+  float* running_pulled;      // snapshot for the next push
+  long long n, lo, total, decay_end;
+};
+cudaError_t ps_apply(const PsApplyArgs& a, int opt, cudaStream_t s);
+cudaError_t ps_push_slot(const PsPushArgs& a, int grid, cudaStream_t s);
+cudaError_t ps_pull_model(const PsPullArgs& a, int grid, cudaStream_t s);
 
 // ---- small direct kernels (smallops.cu): MNIST conv (Cin=1), depthwise 3x3
 cudaError_t conv3x3_c1_fwd(const void* x, const void* w, const float* bias, void* y, int N, int H,

@@ -111,8 +111,27 @@ __global__ void __launch_bounds__(512, 1) allreduce_opt_kernel(const AllreduceOp
   const long long lo = a.begin + min(n, chunk * rank);
   const long long hi = a.begin + min(n, chunk * (rank + 1));
 
-  for (long long i = lo + (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
-       i < hi; i += static_cast<long long>(gridDim.x) * blockDim.x * 8) {
+  // NVLS: a thread keeps kU x 2 multimem.ld_reduce (32 bytes each, reduced in the switch) in
+  // flight; the peer-to-peer path already has 2 x world loads per element group in flight
+  constexpr int kU = MULTIMEM ? 4 : 1;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * 8;
+  for (long long i0 = lo + (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
+       i0 < hi; i0 += stride * kU) {
+   float4 mg0[kU], mg1[kU];
+   if (MULTIMEM) {
+#pragma unroll
+     for (int u = 0; u < kU; ++u) {
+       const long long iu = i0 + u * stride;
+       if (iu < hi) {
+         mg0[u] = multimem_ld_reduce_f32x4(a.grads_mc + iu);
+         mg1[u] = multimem_ld_reduce_f32x4(a.grads_mc + iu + 4);
+       }
+     }
+   }
+#pragma unroll
+   for (int u = 0; u < kU; ++u) {
+    const long long i = i0 + u * stride;
+    if (i >= hi) break;
     float g[8];
     if (world == 1) {
       const float4 g0 = *reinterpret_cast<const float4*>(a.grads[0] + i);
@@ -120,8 +139,7 @@ __global__ void __launch_bounds__(512, 1) allreduce_opt_kernel(const AllreduceOp
       g[0] = g0.x, g[1] = g0.y, g[2] = g0.z, g[3] = g0.w;
       g[4] = g1.x, g[5] = g1.y, g[6] = g1.z, g[7] = g1.w;
     } else if (MULTIMEM) {
-      const float4 g0 = multimem_ld_reduce_f32x4(a.grads_mc + i);
-      const float4 g1 = multimem_ld_reduce_f32x4(a.grads_mc + i + 4);
+      const float4 g0 = mg0[u], g1 = mg1[u];
       g[0] = g0.x, g[1] = g0.y, g[2] = g0.z, g[3] = g0.w;
       g[4] = g1.x, g[5] = g1.y, g[6] = g1.z, g[7] = g1.w;
     } else {
@@ -198,6 +216,10 @@ __global__ void __launch_bounds__(512, 1) allreduce_opt_kernel(const AllreduceOp
       lo4.z = __float_as_uint(w[2]), lo4.w = __float_as_uint(w[3]);
       hi4.x = __float_as_uint(w[4]), hi4.y = __float_as_uint(w[5]);
       hi4.z = __float_as_uint(w[6]), hi4.w = __float_as_uint(w[7]);
+      if (MULTIMEM && a.aux32_mc != nullptr) {
+        multimem_st_b32x4(a.aux32_mc + ai, lo4);
+        multimem_st_b32x4(a.aux32_mc + ai + 4, hi4);
+      } else
 #pragma unroll
       for (int p = 0; p < kMaxRanks; ++p)
         if (p < world) {
@@ -215,6 +237,7 @@ __global__ void __launch_bounds__(512, 1) allreduce_opt_kernel(const AllreduceOp
       *reinterpret_cast<float4*>(a.grads[0] + i) = make_float4(0.f, 0.f, 0.f, 0.f);
       *reinterpret_cast<float4*>(a.grads[0] + i + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+   }
   }
 
   if (world > 1) {
@@ -374,6 +397,127 @@ ps_pull_kernel(const float* __restrict__ w_ps, float* __restrict__ w_local,
   }
 }
 
+// ------------------------------------------- parameter server with optimizer state
+// (parallel/ps.py "slot mode").  The PS GPU owns fp32 parameters + optimizer state + a bf16
+// serving copy; every worker owns two gradient slots in the PS GPU's memory.
+//   worker:  ps_push_slot  - waits (device side, bounded) until its slot has been applied, stores
+//            its fp32 gradients into the slot with one-way NVLink writes, appends the batch-norm
+//            running-statistics deltas, publishes a sequence number with st.release.sys;
+//   server:  ps_apply      - applies SGD / momentum / Adam of ONE slot to the resident state at
+//            HBM speed, refreshes the bf16 serving copy, marks the slot applied;
+//   worker:  ps_pull_model - peer loads of the bf16 weights + the fp32 tail (BN scale/offset,
+//            biases, running statistics).
+// No barrier anywhere: workers never wait for each other (asynchronous SGD), only for their own
+// slot (back-pressure when the server falls behind).
+template <int OPT>
+__global__ void __launch_bounds__(512) ps_apply_kernel(const PsApplyArgs a) {
+  __shared__ float h[8];
+  if (threadIdx.x < 8) h[threadIdx.x] = a.hyper[threadIdx.x];
+  __syncthreads();
+  for (long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < a.n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x * 4) {
+    const float4 g4 = *reinterpret_cast<const float4*>(a.slot + i);
+    float4 w4 = *reinterpret_cast<const float4*>(a.master + i);
+    float g[4] = {g4.x, g4.y, g4.z, g4.w};
+    float w[4] = {w4.x, w4.y, w4.z, w4.w};
+    const long long gi = a.lo + i;           // global element index of this server's slice
+    if (gi >= a.ema_begin) {
+      // non-trainable tail: the slot carries (pulled - locally updated) running statistics
+#pragma unroll
+      for (int j = 0; j < 4; ++j) w[j] -= g[j];
+    } else {
+      float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+      if (OPT != kOptSgd) {
+        const float4 m = *reinterpret_cast<const float4*>(a.state1 + i);
+        s1[0] = m.x, s1[1] = m.y, s1[2] = m.z, s1[3] = m.w;
+      }
+      if (OPT == kOptAdam) {
+        const float4 v = *reinterpret_cast<const float4*>(a.state2 + i);
+        s2[0] = v.x, s2[1] = v.y, s2[2] = v.z, s2[3] = v.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        w[j] = opt_update<OPT>(w[j], g[j], s1[j], s2[j], h, gi + j < a.decay_end);
+      if (OPT != kOptSgd)
+        *reinterpret_cast<float4*>(a.state1 + i) = make_float4(s1[0], s1[1], s1[2], s1[3]);
+      if (OPT == kOptAdam)
+        *reinterpret_cast<float4*>(a.state2 + i) = make_float4(s2[0], s2[1], s2[2], s2[3]);
+    }
+    *reinterpret_cast<float4*>(a.master + i) = make_float4(w[0], w[1], w[2], w[3]);
+    uint2 pk;
+    pk.x = pack_bf16x2(w[0], w[1]);
+    pk.y = pack_bf16x2(w[2], w[3]);
+    *reinterpret_cast<uint2*>(a.wbf16 + i) = pk;
+  }
+  // the last block publishes "slot applied" (workers poll it over NVLink before reusing the slot)
+  __threadfence_system();
+  __syncthreads();
+  __shared__ uint32_t is_last;
+  if (threadIdx.x == 0) is_last = (atomicAdd(a.block_counter, 1u) == gridDim.x - 1) ? 1u : 0u;
+  __syncthreads();
+  if (is_last && threadIdx.x == 0) {
+    *a.block_counter = 0;
+    st_release_sys(a.applied_flag, a.seq);
+  }
+}
+
+__global__ void __launch_bounds__(512) ps_push_slot_kernel(const PsPushArgs a) {
+  // back-pressure: the slot is free once the server has applied what this worker last put there
+  if (threadIdx.x == 0) wait_flag(a.applied_flag, a.need_applied);
+  __syncthreads();
+  const long long nvec = a.n / 4;   // slices and tails are multiples of 8 elements
+  for (long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < nvec;
+       v += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long i = v * 4;      // index inside this server's slice
+    const long long gi = a.lo + i;  // global index
+    uint4 val;
+    if (gi < a.total) {
+      val = *reinterpret_cast<const uint4*>(a.grads + gi);
+    } else {
+      const long long r = gi - a.total;
+      const float4 before = *reinterpret_cast<const float4*>(a.running_pulled + r);
+      const float4 after = *reinterpret_cast<const float4*>(a.running + r);
+      val.x = __float_as_uint(before.x - after.x), val.y = __float_as_uint(before.y - after.y);
+      val.z = __float_as_uint(before.z - after.z), val.w = __float_as_uint(before.w - after.w);
+    }
+    st_relaxed_sys_v4(a.slot + i, val);
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ uint32_t is_last;
+  if (threadIdx.x == 0) is_last = (atomicAdd(a.block_counter, 1u) == gridDim.x - 1) ? 1u : 0u;
+  __syncthreads();
+  if (is_last && threadIdx.x == 0) {
+    *a.block_counter = 0;
+    st_release_sys(a.ready_flag, a.seq);
+  }
+}
+
+__global__ void __launch_bounds__(512) ps_pull_model_kernel(const PsPullArgs a) {
+  const long long nvec = a.n / 8;
+  for (long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < nvec;
+       v += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long i = v * 8;
+    const long long gi = a.lo + i;
+    if (gi < a.total)   // bf16 serving copy: 8 weights per 16-byte load
+      *reinterpret_cast<uint4*>(a.weights + gi) = ld_relaxed_sys_v4(a.wbf16 + i);
+    if (gi >= a.decay_end) {  // fp32 tail: BN scale/offset + biases, then the running statistics
+      const uint4 lo4 = ld_relaxed_sys_v4(a.master + i);
+      const uint4 hi4 = ld_relaxed_sys_v4(a.master + i + 4);
+      if (gi < a.total) {
+        *reinterpret_cast<uint4*>(a.aux32 + (gi - a.decay_end)) = lo4;
+        *reinterpret_cast<uint4*>(a.aux32 + (gi - a.decay_end) + 4) = hi4;
+      } else {
+        const long long r = gi - a.total;
+        *reinterpret_cast<uint4*>(a.running + r) = lo4;
+        *reinterpret_cast<uint4*>(a.running + r + 4) = hi4;
+        *reinterpret_cast<uint4*>(a.running_pulled + r) = lo4;
+        *reinterpret_cast<uint4*>(a.running_pulled + r + 4) = hi4;
+      }
+    }
+  }
+}
+
 template <int OPT>
 cudaError_t launch_ar(const AllreduceOptArgs& a, int grid, cudaStream_t s) {
   if (a.grads_mc != nullptr && a.weights_mc != nullptr && a.world > 1)
@@ -418,6 +562,28 @@ cudaError_t ps_push_sparse(float* w_ps, const float* g_rows, const int* idx, int
   if (blocks < 1) blocks = 1;
   ps_push_sparse_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(w_ps, g_rows, idx, nrows,
                                                                      width, hyper);
+  return cudaGetLastError();
+}
+cudaError_t ps_apply(const PsApplyArgs& a, int opt, cudaStream_t s) {
+  if ((a.n & 7) != 0 || (a.lo & 7) != 0) return cudaErrorInvalidValue;
+  const int grid = 148 * 2;
+  switch (opt) {
+    case kOptSgd: ps_apply_kernel<kOptSgd><<<grid, 512, 0, s>>>(a); break;
+    case kOptMomentum: ps_apply_kernel<kOptMomentum><<<grid, 512, 0, s>>>(a); break;
+    case kOptAdam: ps_apply_kernel<kOptAdam><<<grid, 512, 0, s>>>(a); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+cudaError_t ps_push_slot(const PsPushArgs& a, int grid, cudaStream_t s) {
+  if ((a.n & 7) != 0 || (a.lo & 7) != 0 || (a.total & 7) != 0) return cudaErrorInvalidValue;
+  ps_push_slot_kernel<<<grid, 512, 0, s>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t ps_pull_model(const PsPullArgs& a, int grid, cudaStream_t s) {
+  if ((a.n & 7) != 0 || (a.lo & 7) != 0 || (a.total & 7) != 0 || (a.decay_end & 7) != 0)
+    return cudaErrorInvalidValue;
+  ps_pull_model_kernel<<<grid, 512, 0, s>>>(a);
   return cudaGetLastError();
 }
 cudaError_t ps_pull(const float* w_ps, float* w_local, void* w_bf16, long long n, cudaStream_t s) {

@@ -64,7 +64,8 @@ class ClusterServer(object):
         time.sleep(3600)
 
 
-def start_cluster_server(ctx, num_gpus=1, rdma=False, backend=None, async_ps=None, params=None):
+def start_cluster_server(ctx, num_gpus=1, rdma=False, backend=None, async_ps=None, params=None,
+                         **ps_kwargs):
   """Join this node to the cluster's communication substrate.
 
   Returns ``(cluster_spec, server)`` like the reference.  With ``num_ps == 0`` every worker
@@ -80,7 +81,8 @@ def start_cluster_server(ctx, num_gpus=1, rdma=False, backend=None, async_ps=Non
   if async_ps:
     from .parallel import ps as ps_mod
     # ps nodes need the parameter count (or initial values); workers just attach
-    handle = ps_mod.attach(ctx, params=params)
+    # (``optimizer=...`` + hyper-parameters: the ps keeps the optimizer state - "slot mode")
+    handle = ps_mod.attach(ctx, params=params, **ps_kwargs)
     return ctx.cluster_spec, ClusterServer(ctx, ps=handle)
   group = process_group.init_from_ctx(ctx, backend=backend)
   return ctx.cluster_spec, ClusterServer(ctx, group=group)
@@ -161,7 +163,36 @@ class DataFeed(object):
         raise RuntimeError("feeder posted a ring block but no ring is registered")
       from . import shmring
       self._ring = shmring.attach(info["name"])
+      if getattr(self, "_want_pin", False):
+        try:
+          self._ring.pin()
+          logger.info("feed ring %s page-locked: batches are DMA'd straight from its slots",
+                      info["name"])
+        except Exception as e:
+          logger.warning("could not page-lock the feed ring: %s", e)
+          self._want_pin = False
     return self._ring
+
+  def pin_ring(self):
+    """Page-lock the shared-memory feed ring in THIS process (``cudaHostRegister``), so that the
+    zero-copy views returned by :meth:`next_batch_arrays` are DMA sources: the prefetcher then
+    issues ``cudaMemcpyAsync`` straight from the ring slot and skips its staging copy
+    (feed.DevicePrefetcher.push_arrays).  A slot is therefore kept one call longer (3 instead
+    of 2): it may only go back to the feeders after the copy that reads it has completed, which
+    the prefetcher's back-pressure guarantees two pushes later.  Returns True when pinned."""
+    try:
+      import torch
+      if not torch.cuda.is_available():
+        return False
+      self._want_pin = True
+      self.HOLD_CALLS = max(self.HOLD_CALLS, 3)
+      if _value(self.mgr.get("ring")):
+        self._attach_ring()
+      return True
+    except Exception as e:   # an unpinned ring only costs the staging copy
+      logger.warning("could not page-lock the feed ring: %s", e)
+      self._want_pin = False
+      return False
 
   def _expand(self, item):
     """Turn one queue item into a block: ('rows', list) or ('cols', [ndarray per column], tupled).

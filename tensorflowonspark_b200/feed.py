@@ -34,6 +34,7 @@ class DevicePrefetcher(object):
                                .element_size() for (s, dt) in specs)
     self._specs = specs
     self._host = None   # pinned staging owned by the prefetcher (push_arrays)
+    self.direct_copies = self.staged_copies = 0   # tensors DMA'd in place / through staging
 
   def push_arrays(self, arrays):
     """Stage one batch given as numpy arrays / CPU tensors (e.g. zero-copy views of a feed-ring
@@ -51,12 +52,42 @@ class DevicePrefetcher(object):
     if self._used[i]:
       self.ready[i].synchronize()
     import numpy as np
-    for dst, src in zip(self._host[i], arrays):
+    sources = []
+    for dst, src, (shape, dt) in zip(self._host[i], arrays, self._specs):
       a = src.numpy() if isinstance(src, torch.Tensor) else np.asarray(src)
+      # a view of a page-locked region (the feed ring after DataFeed.pin_ring(), or any pinned
+      # tensor) of the right dtype is a DMA source as it is: no staging copy
+      if a.flags["C_CONTIGUOUS"] and a.size == dst.numel():
+        try:
+          t = torch.from_numpy(a.reshape(dst.shape))
+          if t.dtype == dt and t.is_pinned():
+            sources.append(t)
+            self.direct_copies += 1
+            continue
+        except (TypeError, ValueError, RuntimeError):
+          pass
       # plain single-threaded memcpy (or cast): torch's copy_ fans a 3 MB copy out over the
       # whole intra-op pool, which crawls when several node processes share a CPU quota
       np.copyto(dst.numpy(), a.reshape(dst.shape), casting="unsafe")
-    self.push(self._host[i])
+      sources.append(dst)
+      self.staged_copies += 1
+    self.push(sources)
+
+  def acquire_host(self):
+    """The page-locked staging tensors of the NEXT push, for callers that assemble a batch in
+    place (row by row) instead of handing over ready arrays; waits for the copy that last read
+    them (same back-pressure as :meth:`push_arrays`).  Follow with :meth:`push_host`."""
+    if self._host is None:
+      self._host = [[torch.empty(s, dtype=dt).pin_memory() for (s, dt) in self._specs]
+                    for _ in range(self.depth)]
+    i = self._w
+    if self._used[i]:
+      self.ready[i].synchronize()
+    return self._host[i]
+
+  def push_host(self):
+    self.staged_copies += len(self._specs)
+    self.push(self._host[self._w])
 
   def push(self, host_tensors):
     """Enqueue an async copy of one batch (pinned host tensors) into the next staging slot."""

@@ -406,6 +406,29 @@ class ServedResNet(object):
     if n < self.B:   # ragged tail: pad (the padded rows' outputs are dropped)
       x = np.concatenate([x, np.zeros((self.B - n,) + x.shape[1:], dtype=x.dtype)])
     self.feeder.push_arrays([x])
+    self._enqueue(n)
+
+  def submit_rows(self, columns):
+    """Same as :meth:`submit` for a column of raw row cells (bytes / memoryview / ndarray, one
+    uint8 HWC image each): every row is copied ONCE, straight into the page-locked staging
+    buffer the H2D copy reads - no intermediate batch array (pipeline._run_model uses this when a
+    served model offers it)."""
+    import numpy as np
+    rows = columns["image"] if isinstance(columns, dict) else columns
+    n = len(rows)
+    if n > self.B:
+      raise ValueError("batch of {} rows exceeds the served batch size {}".format(n, self.B))
+    (host,) = self.feeder.acquire_host()
+    hv = host.numpy().reshape(self.B, -1)
+    for r, row in enumerate(rows):
+      hv[r] = np.frombuffer(row, dtype=np.uint8) if not isinstance(row, np.ndarray) \
+          else row.reshape(-1)
+    if n < self.B:
+      hv[n:] = 0
+    self.feeder.push_host()
+    self._enqueue(n)
+
+  def _enqueue(self, n):
     (dx,) = self.feeder.pop()
     self.net.set_input(dx)
     self.feeder.release()

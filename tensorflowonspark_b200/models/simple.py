@@ -59,6 +59,45 @@ def build_echo(state, prefix="out_"):
   return Echo(prefix)
 
 
+class RowSum(object):
+  """Pipelined serving stub with the same protocol as the GPU replicas (``submit_rows`` /
+  ``submit`` / ``collect``): per row, the sum of the bytes of its binary ``image`` cell.  Lets the
+  one-batch-ahead driver in pipeline._run_model be tested on a CPU host."""
+
+  export_builder = "tensorflowonspark_b200.models.simple:build_rowsum"
+  export_builder_args = {}
+  export_signatures = {"serving_default": {"inputs": {"image": "image"},
+                                           "outputs": {"total": "total"},
+                                           "input_dtypes": {"image": "uint8"}}}
+
+  def __init__(self):
+    self._q = []
+    self.max_in_flight = 0
+
+  def state_dict(self):
+    return {}
+
+  def submit_rows(self, columns):
+    import numpy as np
+    self._q.append(np.asarray([int(np.frombuffer(r, dtype=np.uint8).sum())
+                               for r in columns["image"]], dtype=np.int64))
+    self.max_in_flight = max(self.max_in_flight, len(self._q))
+
+  def submit(self, inputs):
+    self._q.append(inputs["image"].astype("int64").sum(axis=1))
+
+  def collect(self):
+    return {"total": self._q.pop(0)}
+
+  def __call__(self, **inputs):
+    self.submit(inputs)
+    return self.collect()
+
+
+def build_rowsum(state):
+  return RowSum()
+
+
 def allreduce_mean_grads(module, world_size):
   """Plain torch.distributed gradient averaging (the CPU/gloo plumbing path and the NCCL
   baseline; the B200 product path is parallel/fused_optim.py)."""

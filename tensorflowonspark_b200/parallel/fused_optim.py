@@ -76,7 +76,16 @@ class FusedOptimizer(object):
         d["flags"] = comm.flag_ptrs()
         d["epoch"] = comm.epoch_ptr(slot)
         d["block_counter"] = comm.counter_ptr(slot)
+        # NVLS: one multimem.ld_reduce through the switch replaces the world peer loads, one
+        # multimem.st the world peer stores (selected when the buffers have multicast addresses)
+        mc = getattr(comm, "mc_ptr", None)
+        if mc is not None and comm.mc_ptr("grads") and comm.mc_ptr("weights"):
+          d["grads_mc"] = comm.mc_ptr("grads")
+          d["weights_mc"] = comm.mc_ptr("weights")
+          d["aux32_mc"] = comm.mc_ptr("aux32")
+          d["grid"] = grid or 48
       self._args.append(d)
+    self.nvls = bool(self._args and self._args[0].get("grads_mc"))
     self._by_tag = {}
     for i, (_, _, tag) in enumerate(self.buckets):
       self._by_tag.setdefault(tag, []).append(i)

@@ -334,24 +334,41 @@ def _run_model(iterator, args, tf_args):
     return zip(*cols)
 
   pipelined = hasattr(model, "submit") and hasattr(model, "collect")
+  raw_rows = pipelined and hasattr(model, "submit_rows")
   waiting = []                  # row counts of the batches submitted but not yet collected
-  for tensors in yield_batch(iterator, args.batch_size, len(in_names)):
-    inputs = {name: _column_to_array(col, dtypes.get(name), shapes.get(name))
-              for name, col in zip(in_names, tensors)}
-    n = len(tensors[0])
-    if pipelined:
-      model.submit(inputs)
+  try:
+    for tensors in yield_batch(iterator, args.batch_size, len(in_names)):
+      n = len(tensors[0])
+      if not pipelined:
+        inputs = {name: _column_to_array(col, dtypes.get(name), shapes.get(name))
+                  for name, col in zip(in_names, tensors)}
+        outputs = model(**inputs) if callable(model) else _apply_state(model, inputs)
+        for row in emit(outputs, n):
+          yield row
+        continue
+      if raw_rows:
+        # the model assembles the batch itself, row cells -> its page-locked staging (one copy)
+        model.submit_rows(dict(zip(in_names, tensors)))
+      else:
+        model.submit({name: _column_to_array(col, dtypes.get(name), shapes.get(name))
+                      for name, col in zip(in_names, tensors)})
       waiting.append(n)
       if len(waiting) > 1:
         for row in emit(model.collect(), waiting.pop(0)):
           yield row
-    else:
-      outputs = model(**inputs) if callable(model) else _apply_state(model, inputs)
-      for row in emit(outputs, n):
+    while waiting:
+      for row in emit(model.collect(), waiting.pop(0)):
         yield row
-  while waiting:
-    for row in emit(model.collect(), waiting.pop(0)):
-      yield row
+  finally:
+    # a consumer that stops early (take / first) abandons this generator with batches still in
+    # flight; the model object is cached per executor, so its queue must not leak into the next
+    # partition's results
+    while waiting:
+      waiting.pop(0)
+      try:
+        model.collect()
+      except Exception:
+        break
 
 
 def _apply_state(state, inputs):

@@ -866,7 +866,17 @@ class RDD(object):
     return functools.reduce(f, vals)
 
   def take(self, num):
-    return self.collect()[:num]
+    """First ``num`` elements, scanning partitions one at a time and pulling only as many
+    elements through the lineage as are needed (Spark semantics: ``take`` must not evaluate the
+    whole RDD - a DataFrame of image rows is GBs)."""
+    out = []
+    for p in self._partitions:
+      if len(out) >= num:
+        break
+      want = num - len(out)
+      part = RDD(self.ctx, [p])
+      out.extend(self.ctx._run_job(part, lambda it, k=want: list(itertools.islice(it, k)))[0])
+    return out[:num]
 
   def first(self):
     r = self.take(1)

@@ -812,6 +812,102 @@ def resnet50_grad_parity():
   return ok
 
 
+@check
+def ps_kernels():
+  """Parameter-server kernels against plain PyTorch: v1 (remote red.add SGD, dense + sparse, pull)
+  and slot mode (push_slot -> ps_apply with SGD / momentum / Adam + weight decay + the
+  non-trainable tail -> pull_model).  Server and client share this process and GPU: the kernels
+  are the same ones that run across NVLink, only the pointers are local."""
+  import numpy as np
+  import torch
+  from tensorflowonspark_b200 import reservation
+  from tensorflowonspark_b200.parallel import ps
+  ok = True
+  srv = reservation.Server(1)
+  addr = srv.start()
+
+  class Ctx(object):
+    def __init__(self, job, idx, cid):
+      self.job_name, self.task_index = job, idx
+      self.cluster_spec = {"ps": ["a:1"], "chief": ["c:3"], "worker": ["d:4", "e:5"]}
+      self.cluster_id, self.server_addr, self.gpus = cid, addr, [0]
+
+  # ---- v1: Hogwild SGD by remote reductions
+  n = 1 << 20
+  w0 = torch.randn(n, device="cuda")
+  server = ps.PSServer(Ctx("ps", 0, "v1"), n, w0)
+  client = ps.PSClient(Ctx("worker", 0, "v1"), local_servers=[server])
+  g = torch.randn(n, device="cuda")
+  client.push(g, lr=0.1, scale=0.5)
+  f32, b16 = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda", dtype=torch.bfloat16)
+  client.pull(out_fp32=f32, out_bf16=b16)
+  torch.cuda.synchronize()
+  ref = w0 - 0.05 * g
+  ok &= _report("ps v1 push_dense + pull fp32", _rel(f32, ref), 1e-6)
+  ok &= _report("ps v1 pull bf16", _rel(b16, ref), 1e-2)
+  rows, width, base = 4096, 64, 128
+  idx = torch.randint(0, rows, (512,), device="cuda")
+  gr = torch.randn(512, width, device="cuda")
+  client.push_sparse(gr, idx, width, base=base, lr=1.0)
+  client.pull(out_fp32=f32)
+  torch.cuda.synchronize()
+  ref2 = ref.clone()
+  ref2[base:base + rows * width].view(rows, width).index_add_(0, idx, -gr)
+  ok &= _report("ps v1 push_sparse (duplicate rows add up)", _rel(f32, ref2), 1e-5)
+  client.close()
+
+  # ---- slot mode
+  total, decay_end, R = 1 << 18, 3 << 16, 1 << 10
+  numel = total + R
+  for opt in ("sgd", "momentum", "adam"):
+    torch.manual_seed(5)
+    init = torch.randn(numel, device="cuda")
+    server = ps.PSServer(Ctx("ps", 0, "slot-" + opt), numel, init, optimizer=opt, lr=0.05,
+                         momentum=0.9, weight_decay=1e-2, decay_end=decay_end, ema_begin=total,
+                         grad_scale=0.5)
+    clients = [ps.PSClient(Ctx(j, i, "slot-" + opt), local_servers=[server])
+               for j, i in (("chief", 0), ("worker", 0), ("worker", 1))]
+    weights = torch.zeros(total, device="cuda", dtype=torch.bfloat16)
+    aux = torch.zeros(total - decay_end, device="cuda")
+    w = init.double().clone()
+    m, v, t = torch.zeros_like(w), torch.zeros_like(w), 0
+    for step in range(3):
+      for c in clients:
+        running = torch.zeros(R, device="cuda")
+        c.pull_model(weights, aux, running, decay_end=decay_end, total=total)
+        torch.cuda.synchronize()
+        ok &= _report("ps slot[{}] pull: bf16 weights".format(opt), _rel(weights, w[:total]), 1e-2)
+        ok &= _report("ps slot[{}] pull: fp32 tail".format(opt),
+                      _rel(aux, w[decay_end:total]) + _rel(running, w[total:]), 1e-5)
+        grads = torch.randn(total, device="cuda")
+        running += 0.1 * torch.randn(R, device="cuda")      # the step moved the running stats
+        c.push_grads(grads, running, total=total)
+        torch.cuda.synchronize()
+        assert server.poll_once() == 1
+        torch.cuda.synchronize()
+        gg = grads.double() * 0.5
+        gg[:decay_end] += 1e-2 * w[:decay_end]
+        if opt == "momentum":
+          m[:total] = 0.9 * m[:total] + gg
+          gg = m[:total]
+        elif opt == "adam":
+          t += 1
+          m[:total] = 0.9 * m[:total] + 0.1 * gg
+          v[:total] = 0.999 * v[:total] + 0.001 * gg * gg
+          gg = (m[:total] / (1 - 0.9 ** t)) / (torch.sqrt(v[:total] / (1 - 0.999 ** t)) + 1e-7)
+        w[:total] -= 0.05 * gg
+        w[total:] = running.double()          # pulled - (pulled - new) = the worker's new values
+    torch.cuda.synchronize()
+    ok &= _report("ps slot[{}] master after 9 applies".format(opt), _rel(server.master, w),
+                  2e-3 if opt == "adam" else 1e-5)
+    ok &= _report("ps slot[{}] applied flags".format(opt),
+                  float((server.applied.cpu() != server.ready.cpu()).sum()), 0.5)
+    for c in clients:
+      c.close()
+  srv.stop()
+  return ok
+
+
 def main():
   names = sys.argv[1:]
   if names:

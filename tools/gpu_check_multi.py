@@ -22,6 +22,7 @@ def rel(a, b):
 
 
 def main():
+  os.environ.setdefault("TFOS_NVLS", "1")   # exercise the multicast path at any world size
   rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
   local = int(os.environ.get("LOCAL_RANK", rank))
   torch.cuda.set_device(local)
@@ -64,24 +65,36 @@ def main():
   # ---- fused all-reduce + optimizer
   N = (25_557_032 + 7) // 8 * 8 if os.environ.get("TFOS_FULL", "1") == "1" else 1 << 20
   decay_end = N // 2 // 8 * 8
-  for opt, name in ((0, "sgd"), (1, "momentum"), (2, "adam")):
+  if rank == 0:
+    print("NVLS multicast substrate:", "available (cuMem VMM + cuMulticast)" if comm.nvls
+          else "not available on this box / disabled: peer-to-peer path only", flush=True)
+  variants = [(0, "sgd", False), (1, "momentum", False), (2, "adam", False)]
+  if comm.nvls:   # the same kernels through multimem.ld_reduce / multimem.st
+    variants += [(1, "momentum", True), (2, "adam", True)]
+  for vi, (opt, name, nvls) in enumerate(variants):
+    if nvls:
+      name += "[nvls]"
     torch.manual_seed(1234)
     w0 = torch.randn(N, device=dev)
     torch.manual_seed(100 + rank)
     g_local = torch.randn(N, device=dev)
-    grads = comm.alloc("g%d" % opt, N, torch.float32)
-    weights = comm.alloc("w%d" % opt, N, torch.bfloat16)
-    aux = comm.alloc("a%d" % opt, N - decay_end, torch.float32)
+    grads = comm.alloc("g%d" % vi, N, torch.float32, multicast=nvls)
+    weights = comm.alloc("w%d" % vi, N, torch.bfloat16, multicast=nvls)
+    aux = comm.alloc("a%d" % vi, N - decay_end, torch.float32, multicast=nvls)
     grads.copy_(g_local)
     master = w0.clone()
     s1, s2 = torch.zeros(N, device=dev), torch.zeros(N, device=dev)
     hyper = torch.tensor([0.1, 0.9, 1e-2, 1.0 / world, 0.9, 0.999, 1e-7, 1.0], device=dev)
     d = {"master": master.data_ptr(), "state1": s1.data_ptr(), "state2": s2.data_ptr(),
          "hyper": hyper.data_ptr(), "begin": 0, "end": N, "decay_end": decay_end, "world": world,
-         "rank": rank, "slot": opt, "opt": opt, "grid": 64,
-         "grads": comm.peer_ptrs("g%d" % opt), "weights": comm.peer_ptrs("w%d" % opt),
-         "aux32": comm.peer_ptrs("a%d" % opt), "aux_begin": decay_end, "flags": comm.flag_ptrs(),
-         "epoch": comm.epoch_ptr(opt), "block_counter": comm.counter_ptr(opt)}
+         "rank": rank, "slot": vi, "opt": opt, "grid": 64,
+         "grads": comm.peer_ptrs("g%d" % vi), "weights": comm.peer_ptrs("w%d" % vi),
+         "aux32": comm.peer_ptrs("a%d" % vi), "aux_begin": decay_end, "flags": comm.flag_ptrs(),
+         "epoch": comm.epoch_ptr(vi), "block_counter": comm.counter_ptr(vi)}
+    if nvls:
+      d.update(grads_mc=comm.mc_ptr("g%d" % vi), weights_mc=comm.mc_ptr("w%d" % vi),
+               aux32_mc=comm.mc_ptr("a%d" % vi))
+      assert d["grads_mc"] and d["weights_mc"] and d["aux32_mc"]
     torch.cuda.synchronize()
     dist.barrier()
     ops.K.allreduce_opt(d)
@@ -121,9 +134,9 @@ def main():
       ms = float(t)
       link_bytes = (world - 1) / world * N * 4 + (world - 1) / world * N * 2  # pulled grads + pushed weights
       if rank == 0:
-        print("TIMING allreduce_momentum N={} world={} {:.3f} ms  {:.1f} GB/s per GPU over NVLink "
+        print("TIMING allreduce_{} N={} world={} {:.3f} ms  {:.1f} GB/s per GPU over NVLink "
               "({:.0f}% of the 770 GB/s measured peer-copy rate)".format(
-                  N, world, ms, link_bytes / ms / 1e6, 100 * link_bytes / ms / 1e6 / 770))
+                  name, N, world, ms, link_bytes / ms / 1e6, 100 * link_bytes / ms / 1e6 / 770))
       # NCCL baseline: all-reduce + unfused update
       gg = g_local.clone()
       torch.cuda.synchronize()
