@@ -352,6 +352,36 @@ def main():
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     exposed = float(t)
 
+  # What the collective really costs INSIDE the captured graph: the same step on the same GPUs
+  # with the communicator removed (N independent replicas, still launched together and timed as
+  # the max over ranks).  step(with comm) - step(without) = exposed communication + barrier skew;
+  # the spread of the no-comm times across ranks is the hardware (clock / power) skew that no
+  # collective can hide.
+  comm_diag = None
+  if world > 1 and not args.no_graph and os.environ.get("TFOS_BENCH_COMM_DIAG", "1") == "1":
+    solo = resnet.ResNetTrainer(depth=50, batch=B, image=args.image, num_classes=1000, device=dev,
+                                lr=0.1 * B / 256.0, momentum=0.9, weight_decay=1e-4, comm=None)
+    solo.set_input(x, y)
+    solo.train_step()
+    solo.capture()
+    for _ in range(3):
+      solo.train_step()
+    sync_all()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(args.steps):
+      solo.train_step()
+    s1.record()
+    sync_all()
+    mine = s0.elapsed_time(s1) / args.steps
+    tmax, tmin = torch.tensor([mine], device=dev), torch.tensor([mine], device=dev)
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+    comm_diag = {"no_comm_ms_per_step_max": float(tmax), "no_comm_ms_per_step_min": float(tmin),
+                 "comm_cost_ms_per_step_in_graph": ms_per_step - float(tmax),
+                 "nvls": bool(getattr(net.optim, "nvls", False))}
+    del solo
+
   if rank == 0:
     out = {
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world,
@@ -378,6 +408,8 @@ def main():
       out["e2e"] = e2e
     if exposed is not None:
       out["exposed_allreduce_ms_per_step"] = exposed
+    if comm_diag is not None:
+      out["comm"] = comm_diag
     print(json.dumps(out))
     sys.stdout.flush()
   watchdog.cancel()

@@ -57,7 +57,13 @@ def run(gpus, batch=256, batches=40, warm_batches=4):
       .set("spark.executor.resource.gpu.amount", "1").set("spark.task.resource.gpu.amount", "1")
   sc = SparkContext(conf=conf)
   spark = SparkSession(sc)
-  sc.parallelize([0], 1).foreachPartition(lambda it: export_model(export_dir))
+  # the artefact is written by a short-lived process so that neither the driver nor an executor
+  # keeps a CUDA context on a GPU before the replicas are placed
+  import subprocess
+  subprocess.run([sys.executable, "-c", "import sys; sys.path.insert(0, {!r}); "
+                  "sys.path.insert(0, {!r}); import inference_resnet50 as m; "
+                  "m.export_model({!r})".format(ROOT, os.path.join(ROOT, "bench"), export_dir)],
+                 check=True, timeout=600)
   schema = StructType([StructField("image", BinaryType())])
 
   def frame(per_part):

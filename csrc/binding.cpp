@@ -88,6 +88,7 @@ tfos::TmapDesc parse_tmap(const py::dict& d) {
 int64_t plan_fwd(const py::dict& a, const py::dict& b, const py::dict& g, int bn, bool b_mn) {
   tfos::FwdArgs f;
   std::memset(&f, 0, sizeof(f));
+  std::memset(&f, 0, sizeof(f));
   f.tiles_w = geti<int>(g, "tiles_w", 1);
   f.tiles_h = geti<int>(g, "tiles_h", 1);
   f.tiles_n = geti<int>(g, "tiles_n", 1);
@@ -124,6 +125,8 @@ int64_t plan_fwd(const py::dict& a, const py::dict& b, const py::dict& g, int bn
   f.col_sum = reinterpret_cast<float*>(geti<uint64_t>(g, "col_sum", 0));
   f.col_sumsq = reinterpret_cast<float*>(geti<uint64_t>(g, "col_sumsq", 0));
   f.out = reinterpret_cast<void*>(geti<uint64_t>(g, "out", 0));
+  f.red_x = reinterpret_cast<const void*>(geti<uint64_t>(g, "red_x", 0));
+  f.red_mask = reinterpret_cast<const uint8_t*>(geti<uint64_t>(g, "red_mask", 0));
   TORCH_CHECK(f.out != nullptr && f.ldo > 0 && f.n_valid > 0, "igemm fwd: out/ldo/n_valid");
   char err[512] = {0};
   tfos::IGemmPlan* p =
@@ -179,6 +182,10 @@ int64_t plan_wgrad(const py::dict& a, const py::dict& b, const py::dict& g, int 
 void plan_run(int64_t h) {
   check(tfos::igemm_run(reinterpret_cast<tfos::IGemmPlan*>(h), cur_stream()), "igemm_run");
 }
+void plan_set_reverse(int64_t h, bool flag) {
+  tfos::igemm_plan_set_reverse(reinterpret_cast<tfos::IGemmPlan*>(h), flag ? 1 : 0);
+}
+void bn_set_row_reverse(bool flag) { tfos::bn_set_row_reverse(flag ? 1 : 0); }
 void plan_free(int64_t h) { tfos::igemm_plan_free(reinterpret_cast<tfos::IGemmPlan*>(h)); }
 py::dict plan_info(int64_t h) {
   auto* p = reinterpret_cast<tfos::IGemmPlan*>(h);
@@ -275,13 +282,14 @@ void bn_bwd_reduce(const Tensor& dy, const Tensor& x, c10::optional<Tensor> y, c
 void bn_bwd_apply(const Tensor& dy, const Tensor& x, c10::optional<Tensor> y, const Tensor& gamma,
                   const Tensor& mean, const Tensor& invstd, const Tensor& dgamma,
                   const Tensor& dbeta, Tensor dx, c10::optional<Tensor> dres, int relu,
-                  c10::optional<Tensor> fscale, c10::optional<Tensor> fshift) {
+                  c10::optional<Tensor> fscale, c10::optional<Tensor> fshift,
+                  c10::optional<Tensor> sum_g, c10::optional<Tensor> sum_gx) {
   const int C = x.size(-1);
   check(tfos::bn_bwd_apply(dy.data_ptr(), x.data_ptr(), optptr(y), gamma.data_ptr<float>(),
                            mean.data_ptr<float>(), invstd.data_ptr<float>(),
                            dgamma.data_ptr<float>(), dbeta.data_ptr<float>(), optf(fscale),
                            optf(fshift), dx.data_ptr(), const_cast<void*>(optptr(dres)),
-                           x.numel() / C, C, relu, cur_stream()),
+                           x.numel() / C, C, relu, optf(sum_g), optf(sum_gx), cur_stream()),
         "bn_bwd_apply");
 }
 void add_act(const Tensor& a, c10::optional<Tensor> b, Tensor out, int act) {
@@ -469,6 +477,9 @@ tfos::BcastArgs parse_bcast(const py::dict& d) {
 void bcast_pull(const py::dict& d) {
   check(tfos::bcast_pull(parse_bcast(d), geti<int>(d, "grid", 32), cur_stream()), "bcast_pull");
 }
+void set_flag_timeout_ms(double ms) {
+  check(tfos::set_flag_timeout_ns(static_cast<unsigned long long>(ms * 1e6)), "set_flag_timeout_ms");
+}
 void flag_barrier(const py::dict& d) {
   check(tfos::flag_barrier(parse_bcast(d), cur_stream()), "flag_barrier");
 }
@@ -598,6 +609,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("igemm_plan_wgrad", &plan_wgrad);
   m.def("igemm_run", &plan_run);
   m.def("igemm_free", &plan_free);
+  m.def("igemm_set_reverse", &plan_set_reverse);
+  m.def("bn_set_row_reverse", &bn_set_row_reverse);
   m.def("igemm_info", &plan_info);
   m.def("bn_stats", &bn_stats);
   m.def("bn_finalize", &bn_finalize);
@@ -606,7 +619,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("shift"), py::arg("y"), py::arg("act"), py::arg("mask") = py::none());
   m.def("bn_apply_finalize", &bn_apply_finalize);
   m.def("bn_bwd_reduce", &bn_bwd_reduce);
-  m.def("bn_bwd_apply", &bn_bwd_apply);
+  m.def("bn_bwd_apply", &bn_bwd_apply, py::arg("dy"), py::arg("x"), py::arg("y"), py::arg("gamma"),
+        py::arg("mean"), py::arg("invstd"), py::arg("dgamma"), py::arg("dbeta"), py::arg("dx"),
+        py::arg("dres"), py::arg("relu"), py::arg("fscale"), py::arg("fshift"),
+        py::arg("sum_g") = py::none(), py::arg("sum_gx") = py::none());
   m.def("add_act", &add_act);
   m.def("relu_bwd", &relu_bwd);
   m.def("colsum", &colsum);
@@ -625,6 +641,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("allreduce_opt", &allreduce_opt);
   m.def("bcast_pull", &bcast_pull);
   m.def("flag_barrier", &flag_barrier);
+  m.def("set_flag_timeout_ms", &set_flag_timeout_ms);
   m.def("ps_push_dense", &ps_push_dense);
   m.def("ps_push_sparse", &ps_push_sparse);
   m.def("ps_pull", &ps_pull);

@@ -65,7 +65,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
                      const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
                      const float* __restrict__ invstd, const float* __restrict__ fscale,
                      const float* __restrict__ fshift, long long P, int C, int relu, float* dgamma,
-                     float* dbeta) {
+                     float* dbeta, const int rev) {
   const Geo G = geo(C);
   __shared__ float red[2][kThreads][8];
   const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
@@ -94,7 +94,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
         for (int k = 0; k < kRows; ++k) {
           const long long pk = p + k * stride;
           const bool in = pk < P;
-          const long long o = pk * C + c;
+          const long long o = (rev ? P - 1 - pk : pk) * C + c;
           gq[k] = in ? ld_nc_v4(dy + o) : zero;
           xq[k] = in ? ld_nc_v4(x + o) : zero;
           yq[k] = (in && relu == 1) ? ld_nc_v4(y + o) : zero;
@@ -155,10 +155,11 @@ __global__ void __launch_bounds__(kThreads, 2)
 bn_bwd_apply_kernel(const __nv_bfloat16* dy, const __nv_bfloat16* __restrict__ x,
                     const __nv_bfloat16* __restrict__ y, const float* __restrict__ gamma,
                     const float* __restrict__ mean, const float* __restrict__ invstd,
-                    const float* __restrict__ dgamma, const float* __restrict__ dbeta,
+                    float* dgamma, float* dbeta,
                     const float* __restrict__ fscale, const float* __restrict__ fshift,
                     __nv_bfloat16* __restrict__ dx, __nv_bfloat16* dres, long long P, int C,
-                    int relu, float inv_count) {
+                    int relu, float inv_count, const int rev,
+                    const float* __restrict__ sum_g, const float* __restrict__ sum_gx) {
   const Geo G = geo(C);
   if (G.r_in >= G.rl) return;
   const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
@@ -174,9 +175,23 @@ bn_bwd_apply_kernel(const __nv_bfloat16* dy, const __nv_bfloat16* __restrict__ x
       for (int h = 0; h < 2; ++h) {
         const int ch = c + 2 * j + h;
         const float is = invstd[ch];
+        float dg, db;
+        if (sum_g != nullptr) {
+          // the reduction was fused into the producing data gradient's epilogue (igemm.cu):
+          // sum(g) and sum(g x) arrive raw; one thread per channel publishes dgamma / dbeta
+          db = sum_g[ch];
+          dg = is * (sum_gx[ch] - mean[ch] * db);
+          if (blockIdx.x == 0 && G.r_in == 0) {
+            dgamma[ch] = dg;
+            dbeta[ch] = db;
+          }
+        } else {
+          dg = dgamma[ch];
+          db = dbeta[ch];
+        }
         a[h] = gamma[ch] * is;
-        b[h] = -a[h] * is * dgamma[ch] * inv_count;
-        kk[h] = -a[h] * dbeta[ch] * inv_count - b[h] * mean[ch];
+        b[h] = -a[h] * is * dg * inv_count;
+        kk[h] = -a[h] * db * inv_count - b[h] * mean[ch];
       }
       cA[j] = make_float2(a[0], a[1]);
       cB[j] = make_float2(b[0], b[1]);
@@ -195,7 +210,7 @@ bn_bwd_apply_kernel(const __nv_bfloat16* dy, const __nv_bfloat16* __restrict__ x
       for (int k = 0; k < kRows; ++k) {
         const long long pk = p + k * stride;
         const bool in = pk < P;
-        const long long o = pk * C + c;
+        const long long o = (rev ? P - 1 - pk : pk) * C + c;
         gq[k] = in ? *reinterpret_cast<const uint4*>(dy + o) : zero;  // may alias dres: no .nc
         xq[k] = in ? ld_nc_v4(x + o) : zero;
         yq[k] = (in && relu == 1) ? ld_nc_v4(y + o) : zero;
@@ -205,7 +220,7 @@ bn_bwd_apply_kernel(const __nv_bfloat16* dy, const __nv_bfloat16* __restrict__ x
       for (int k = 0; k < kRows; ++k) {
         const long long pk = p + k * stride;
         if (pk >= P) break;
-        const long long o = pk * C + c;
+        const long long o = (rev ? P - 1 - pk : pk) * C + c;
         const uint32_t gw[4] = {gq[k].x, gq[k].y, gq[k].z, gq[k].w};
         const uint32_t xw[4] = {xq[k].x, xq[k].y, xq[k].z, xq[k].w};
         const uint32_t yw[4] = {yq[k].x, yq[k].y, yq[k].z, yq[k].w};
@@ -235,7 +250,7 @@ __global__ void __launch_bounds__(kThreads, 3)
 bn_fwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ residual,
                     const float* __restrict__ scale, const float* __restrict__ shift,
                     __nv_bfloat16* __restrict__ y, uint8_t* __restrict__ mask, long long P, int C,
-                    int act, const BnFinalize fin) {
+                    int act, const BnFinalize fin, const int rev) {
   const Geo G = geo(C);
   if (G.r_in >= G.rl) return;
   const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
@@ -289,7 +304,7 @@ bn_fwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __
       for (int k = 0; k < kRows; ++k) {
         const long long pk = p + k * stride;
         const bool in = pk < P;
-        const long long o = pk * C + c;
+        const long long o = (rev ? P - 1 - pk : pk) * C + c;
         xq[k] = in ? ld_nc_v4(x + o) : zero;
         rq[k] = (in && has_res) ? ld_nc_v4(residual + o) : zero;
       }
@@ -297,7 +312,7 @@ bn_fwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __
       for (int k = 0; k < kRows; ++k) {
         const long long pk = p + k * stride;
         if (pk >= P) break;
-        const long long o = pk * C + c;
+        const long long o = (rev ? P - 1 - pk : pk) * C + c;
         const uint32_t xw[4] = {xq[k].x, xq[k].y, xq[k].z, xq[k].w};
         const uint32_t rw[4] = {rq[k].x, rq[k].y, rq[k].z, rq[k].w};
         uint32_t ow[4], bits = 0;
@@ -322,6 +337,12 @@ bn_fwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __
   }
 }
 
+// L2 hand-over hint (see bn_set_row_reverse in ops.h): the next launches walk the rows from the
+// END of the tensor - that is where the kernel that produced (or last read) it stopped, so the
+// first ~L2-size worth of reads hit the 126 MB L2 instead of HBM.  Host state, read at launch
+// time (and therefore baked into a captured CUDA graph).
+int g_row_reverse = 0;
+
 inline dim3 red_grid(long long P, int C, int waves) {
   const int groups = C >> 3;
   const int cg = groups < kThreads ? groups : kThreads;
@@ -342,12 +363,14 @@ inline int env_waves(const char* name, int dflt) {
 
 }  // namespace
 
+void bn_set_row_reverse(int flag) { g_row_reverse = flag ? 1 : 0; }
+
 cudaError_t bn_apply(const void* x, const void* residual, const float* scale, const float* shift,
                      void* y, uint8_t* mask, long long P, int C, int act, cudaStream_t s) {
   static const int waves = env_waves("TFOS_BN_WAVES_FWD", 3);
   bn_fwd_apply_kernel<false><<<red_grid(P, C, waves), kThreads, 0, s>>>(
       static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(residual), scale,
-      shift, static_cast<__nv_bfloat16*>(y), mask, P, C, act, BnFinalize());
+      shift, static_cast<__nv_bfloat16*>(y), mask, P, C, act, BnFinalize(), g_row_reverse);
   return cudaGetLastError();
 }
 
@@ -356,7 +379,7 @@ cudaError_t bn_apply_finalize(const void* x, const void* residual, void* y, uint
   static const int waves = env_waves("TFOS_BN_WAVES_FWD", 3);
   bn_fwd_apply_kernel<true><<<red_grid(P, C, waves), kThreads, 0, s>>>(
       static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(residual), nullptr,
-      nullptr, static_cast<__nv_bfloat16*>(y), mask, P, C, act, fin);
+      nullptr, static_cast<__nv_bfloat16*>(y), mask, P, C, act, fin, g_row_reverse);
   return cudaGetLastError();
 }
 
@@ -368,20 +391,21 @@ cudaError_t bn_bwd_reduce(const void* dy, const void* x, const void* y, const fl
   bn_bwd_reduce_kernel<<<red_grid(P, C, waves), kThreads, 0, s>>>(
       static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x),
       static_cast<const __nv_bfloat16*>(y), mean, invstd, fscale, fshift, P, C, relu, dgamma,
-      dbeta);
+      dbeta, g_row_reverse);
   return cudaGetLastError();
 }
 
 cudaError_t bn_bwd_apply(const void* dy, const void* x, const void* y, const float* gamma,
-                         const float* mean, const float* invstd, const float* dgamma,
-                         const float* dbeta, const float* fscale, const float* fshift, void* dx,
-                         void* dres, long long P, int C, int relu, cudaStream_t s) {
+                         const float* mean, const float* invstd, float* dgamma,
+                         float* dbeta, const float* fscale, const float* fshift, void* dx,
+                         void* dres, long long P, int C, int relu, const float* sum_g,
+                         const float* sum_gx, cudaStream_t s) {
   static const int waves = env_waves("TFOS_BN_WAVES_APPLY", 2);
   bn_bwd_apply_kernel<<<red_grid(P, C, waves), kThreads, 0, s>>>(
       static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x),
       static_cast<const __nv_bfloat16*>(y), gamma, mean, invstd, dgamma, dbeta, fscale, fshift,
       static_cast<__nv_bfloat16*>(dx), static_cast<__nv_bfloat16*>(dres), P, C, relu,
-      1.f / static_cast<float>(P));
+      1.f / static_cast<float>(P), g_row_reverse, sum_g, sum_gx);
   return cudaGetLastError();
 }
 

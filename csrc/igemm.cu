@@ -76,7 +76,8 @@ __device__ __forceinline__ void red_shared_add(float* p, float v) {
 // EPI selects a compile-time epilogue so the common cases carry no per-element flag tests:
 //   0 plain store, 1 fused BN statistics, 2 read-modify-write accumulate,
 //   4 generic (bias / ReLU / ReLU6 / statistics / accumulate decided at run time).
-constexpr int kEpiPlain = 0, kEpiStats = 1, kEpiAccum = 2, kEpiGeneric = 4;
+//   8 (with 0 or 2) fused batch-norm backward reduction over the stored gradient tile.
+constexpr int kEpiPlain = 0, kEpiStats = 1, kEpiAccum = 2, kEpiGeneric = 4, kEpiBnRed = 8;
 
 template <int BN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -166,6 +167,7 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int nt = tile % a.n_tiles;
         int mt = tile / a.n_tiles;
+        if (a.reverse) mt = a.tiles_w * a.tiles_h * a.tiles_n - 1 - mt;
         const int tw = mt % a.tiles_w;
         mt /= a.tiles_w;
         const int th = mt % a.tiles_h;
@@ -264,6 +266,7 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const bool acc_on = kGeneric ? (a.accumulate != 0) : ((EPI & kEpiAccum) != 0);
     const bool bias_on = kGeneric && a.bias != nullptr;
     const bool relu_on = kGeneric && a.relu != 0;
+    constexpr bool red_on = (EPI & kEpiBnRed) != 0;   // fused BN backward reduction (igemm.h)
     const uint32_t stg = smem_u32(out_stage + ew * 4096);
     const bool split = BN == 64 && a.n_tiles == 1;   // half-groups own alternate tiles
     // position of this thread's accumulator row inside the pixel box: tile independent
@@ -304,6 +307,47 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
     };
+    // fused BN backward reduction: lane (r, sg) of the store phase owns the 8 columns of segment
+    // sg for its 8 rows; per slab 8 x (sum g, sum g*x) live in registers until the n tile changes
+    float2 bg[red_on ? kSlabs : 1][4], bgx[red_on ? kSlabs : 1][4];
+#pragma unroll
+    for (int i = 0; i < (red_on ? kSlabs : 1); ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bg[i][j] = bgx[i][j] = make_float2(0.f, 0.f);
+    auto flush_red = [&](int nt) {
+#pragma unroll
+      for (int ci = 0; ci < (red_on ? kSlabs : 1); ++ci) {
+        const int c = split ? ci : half + 2 * ci;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float2 g2 = bg[ci][j], x2 = bgx[ci][j];
+#pragma unroll
+          for (int m = 8; m <= 16; m <<= 1) {   // the four row lanes of a segment meet
+            g2.x += __shfl_xor_sync(0xffffffff, g2.x, m), g2.y += __shfl_xor_sync(0xffffffff, g2.y, m);
+            x2.x += __shfl_xor_sync(0xffffffff, x2.x, m), x2.y += __shfl_xor_sync(0xffffffff, x2.y, m);
+          }
+          if (lane < 8 && c < BN / 64) {
+            float* st = stat_smem + (c * 64 + lane * 8 + 2 * j) * 2;
+            red_shared_add(st + 0, g2.x);
+            red_shared_add(st + 1, x2.x);
+            red_shared_add(st + 2, g2.y);
+            red_shared_add(st + 3, x2.y);
+          }
+          bg[ci][j] = bgx[ci][j] = make_float2(0.f, 0.f);
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int c = et; c < BN; c += kEpiThreads) {
+        const int col = nt * BN + c;
+        if (col < a.n_valid) {
+          atomicAdd(a.col_sum + col, stat_smem[c * 2 + 0]);
+          atomicAdd(a.col_sumsq + col, stat_smem[c * 2 + 1]);
+        }
+        stat_smem[c * 2 + 0] = 0.f;
+        stat_smem[c * 2 + 1] = 0.f;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    };
     int it = -1;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       ++it;
@@ -312,6 +356,7 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t acc_phase = (it >> 1) & 1;
       const int nt = tile % a.n_tiles;
       int mt = tile / a.n_tiles;
+      if (a.reverse) mt = a.tiles_w * a.tiles_h * a.tiles_n - 1 - mt;
       const int tw = mt % a.tiles_w;
       mt /= a.tiles_w;
       const int th = mt % a.tiles_h;
@@ -357,6 +402,27 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
             }
           }
+          // fused BN reduction: x of the batch norm below and its ReLU bits, same rows / segment.
+          // Issued before the TMEM read (latency hidden behind it) unless the accumulate operands
+          // already occupy that slot - prev[] + xq[] + the 64 accumulator words would spill -
+          // then right after the tile has been staged.
+          uint4 xq[red_on ? 8 : 1];
+          uint32_t mq[red_on ? 8 : 1];
+          auto load_red = [&]() {
+            const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(a.red_x);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r2 = i * 4 + (lane >> 3);
+              xq[i] = make_uint4(0u, 0u, 0u, 0u);
+              mq[i] = 0xffu;
+              if ((vmask >> r2) & 1u) {
+                const long long e = roffs[i] + c * 64 + (lane & 7) * 8;
+                xq[i] = *reinterpret_cast<const uint4*>(xb + e);
+                if (a.red_mask != nullptr) mq[i] = a.red_mask[e >> 3];
+              }
+            }
+          };
+          if (red_on && !acc_on) load_red();
           uint32_t v[64];
           {
             uint32_t (&lo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
@@ -395,6 +461,7 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                          "r"(pk[sgm * 4 + 1]), "r"(pk[sgm * 4 + 2]), "r"(pk[sgm * 4 + 3])
                          : "memory");
           }
+          if (red_on && acc_on) load_red();
           __syncwarp();
           if (do_stats) {
             // lane l owns columns (2l, 2l+1) of the slab: word (l & 3) of segment (l >> 2);
@@ -446,6 +513,19 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 val.z = pack_bf16x2(n2.x, n2.y), val.w = pack_bf16x2(n3.x, n3.y);
               }
               *reinterpret_cast<uint4*>(o) = val;
+              if (red_on) {   // statistics of the ROUNDED gradient that was just stored
+                const uint32_t gw[4] = {val.x, val.y, val.z, val.w};
+                const uint32_t xw[4] = {xq[i].x, xq[i].y, xq[i].z, xq[i].w};
+                const uint32_t mb = mq[i];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  float2 g2 = unpack_bf16x2(gw[j]);
+                  g2.x = ((mb >> (2 * j)) & 1u) ? g2.x : 0.f;
+                  g2.y = ((mb >> (2 * j + 1)) & 1u) ? g2.y : 0.f;
+                  bg[ci][j] = __fadd2_rn(bg[ci][j], g2);
+                  bgx[ci][j] = __ffma2_rn(g2, unpack_bf16x2(xw[j]), bgx[ci][j]);
+                }
+              }
             }
           }
           __syncwarp();
@@ -545,9 +625,12 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int next_tile = tile + gridDim.x;
       if (!split && do_stats && (next_tile >= total_tiles || next_tile % a.n_tiles != nt))
         flush_stats(nt);
+      if (!split && red_on && (next_tile >= total_tiles || next_tile % a.n_tiles != nt))
+        flush_red(nt);
     }
     // split mode: the half-groups skip each other's tiles, so they meet only here (one n tile)
     if (split && do_stats && blockIdx.x < total_tiles) flush_stats(0);
+    if (split && red_on && blockIdx.x < total_tiles) flush_red(0);
   }
 
   tc_fence_before();
@@ -626,9 +709,12 @@ cudaError_t launch_fwd(const IGemmPlan* p, cudaStream_t s) {
   const FwdArgs& f = p->fa;
   const bool ragged = f.out_fp32 || (f.ldo & 7) != 0 || (f.n_valid % BN) != 0;
   const bool generic = ragged || f.bias != nullptr || f.relu != 0 ||
-                       (f.col_sum != nullptr && f.accumulate);
+                       (f.col_sum != nullptr && f.accumulate && f.red_x == nullptr);
   if (generic) return launch_fwd_epi<BN, B_MN, kEpiGeneric>(p, s);
   if (B_MN) {  // data gradients: plain or accumulate (statistics only through the generic path)
+    if (f.red_x != nullptr)   // fused BN backward reduction (validated in igemm_plan_fwd)
+      return f.accumulate ? launch_fwd_epi<BN, B_MN, kEpiAccum | kEpiBnRed>(p, s)
+                          : launch_fwd_epi<BN, B_MN, kEpiBnRed>(p, s);
     if (f.col_sum != nullptr) return launch_fwd_epi<BN, B_MN, kEpiGeneric>(p, s);
     return f.accumulate ? launch_fwd_epi<BN, B_MN, kEpiAccum>(p, s)
                         : launch_fwd_epi<BN, B_MN, kEpiPlain>(p, s);
@@ -656,8 +742,15 @@ IGemmPlan* igemm_plan_fwd(const TmapDesc& a, const TmapDesc& b, const FwdArgs& a
     snprintf(err, errlen, "acc_mask needs accumulate, bf16 output and whole column tiles");
     return nullptr;
   }
-  if (args.col_sum != nullptr && args.accumulate) {
+  if (args.col_sum != nullptr && args.accumulate && args.red_x == nullptr) {
     snprintf(err, errlen, "fused statistics cannot be combined with accumulate");
+    return nullptr;
+  }
+  if (args.red_x != nullptr &&
+      (!b_mn || args.col_sum == nullptr || args.col_sumsq == nullptr || args.out_fp32 ||
+       (args.ldo & 7) != 0 || args.n_valid % bn != 0 || args.bias != nullptr || args.relu != 0)) {
+    snprintf(err, errlen, "fused BN reduction needs a data-gradient plan with bf16 output, whole "
+                          "column tiles, no bias / ReLU and both accumulators");
     return nullptr;
   }
   IGemmPlan* p = new (std::nothrow) IGemmPlan();
@@ -778,5 +871,8 @@ cudaError_t igemm_run(const IGemmPlan* p, cudaStream_t s) {
 }
 
 void igemm_plan_free(IGemmPlan* p) { delete p; }
+void igemm_plan_set_reverse(IGemmPlan* p, int flag) {
+  if (p->kind == 0) p->fa.reverse = flag ? 1 : 0;
+}
 
 }  // namespace tfos

@@ -54,6 +54,17 @@ struct FwdArgs {
   // stem mode (7x7/2 convolution on the window-row layout, see igemm.cu): ONE halo box of
   // 2*box_h+5 input rows per tile serves all seven filter rows; box_w must be 8
   int stem;
+  // walk the pixel tiles from the END of the tensor (L2 hand-over: start where the kernel that
+  // produced the A operand stopped writing); the n tile of a CTA is unaffected
+  int reverse;
+  // fused batch-norm backward reduction (data-gradient epilogues): the tile being stored is the
+  // gradient dY of a batch norm whose input was red_x (same layout as ``out``).  Per column the
+  // epilogue accumulates  sum(g)  into col_sum and  sum(g * x)  into col_sumsq, where g = dY
+  // masked by red_mask (one bit per element, the ReLU that followed the batch norm; null = no
+  // ReLU).  bn_bwd_apply turns the two sums into dbeta / dgamma - the stand-alone reduce pass
+  // (a full read of dY and x) disappears.
+  const void* red_x;
+  const uint8_t* red_mask;
 };
 
 // weight-gradient problems: K = pixels, M = Cout, N = Cin (per tap).
@@ -97,5 +108,6 @@ IGemmPlan* igemm_plan_wgrad(const TmapDesc& a, const TmapDesc& b, const WgradArg
                             int num_sms, char* err, int errlen);
 cudaError_t igemm_run(const IGemmPlan* plan, cudaStream_t stream);
 void igemm_plan_free(IGemmPlan* plan);
+void igemm_plan_set_reverse(IGemmPlan* plan, int flag);  // fwd-like plans only
 
 }  // namespace tfos

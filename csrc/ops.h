@@ -18,6 +18,8 @@ cudaError_t bn_inference_coeffs(const float* gamma, const float* beta, const flo
                                 const float* rv, float* scale, float* shift, int C, float eps,
                                 cudaStream_t s);
 // mask (optional): one bit per element, set where the pre-activation value is > 0
+// row order of the following bn_apply / bn_apply_finalize / bn_bwd_* launches: 1 = last row first
+void bn_set_row_reverse(int flag);
 cudaError_t bn_apply(const void* x, const void* residual, const float* scale, const float* shift,
                      void* y, uint8_t* mask, long long P, int C, int act, cudaStream_t s);
 // Same, with the statistics finalisation folded in: every thread derives scale / shift of its
@@ -45,9 +47,10 @@ cudaError_t bn_bwd_reduce(const void* dy, const void* x, const void* y, const fl
                           long long P, int C, int relu, float* dgamma, float* dbeta,
                           cudaStream_t s);
 cudaError_t bn_bwd_apply(const void* dy, const void* x, const void* y, const float* gamma,
-                         const float* mean, const float* invstd, const float* dgamma,
-                         const float* dbeta, const float* fscale, const float* fshift, void* dx,
-                         void* dres, long long P, int C, int relu, cudaStream_t s);
+                         const float* mean, const float* invstd, float* dgamma,
+                         float* dbeta, const float* fscale, const float* fshift, void* dx,
+                         void* dres, long long P, int C, int relu, const float* sum_g,
+                         const float* sum_gx, cudaStream_t s);
 cudaError_t add_act(const void* a, const void* b, void* out, long long n, int act, cudaStream_t s);
 cudaError_t relu_bwd(const void* dy, const void* y, void* dx, long long n, cudaStream_t s);
 cudaError_t colsum(const void* x, long long P, int C, float* out, cudaStream_t s);
@@ -104,6 +107,7 @@ struct BcastArgs {
   uint32_t* block_counter;
 };
 cudaError_t bcast_pull(const BcastArgs& a, int grid, cudaStream_t s);
+cudaError_t set_flag_timeout_ns(unsigned long long ns);  // bound of every device-side peer wait
 cudaError_t flag_barrier(const BcastArgs& a, cudaStream_t s);
 cudaError_t ps_push_dense(float* w_ps, const float* g, long long n, const float* hyper,
                           cudaStream_t s);

@@ -35,6 +35,9 @@ namespace {
 #ifndef TFOS_FLAG_TIMEOUT_NS
 #define TFOS_FLAG_TIMEOUT_NS 20000000000ull
 #endif
+// how long a rank waits for a peer before it gives up (trap -> CUDA error -> node error queue ->
+// driver exception, TFSparkNode.py): runtime knob, TFOS_FLAG_TIMEOUT_MS (parallel/symm.py)
+__device__ unsigned long long g_flag_timeout_ns = TFOS_FLAG_TIMEOUT_NS;
 
 __device__ __forceinline__ void wait_flag(const uint32_t* p, uint32_t target) {
   if (static_cast<int32_t>(ld_acquire_sys(p) - target) >= 0) return;
@@ -43,7 +46,7 @@ __device__ __forceinline__ void wait_flag(const uint32_t* p, uint32_t target) {
   while (static_cast<int32_t>(ld_acquire_sys(p) - target) < 0) {
     if ((++spins & 0xff) == 0) {
       __nanosleep(64);
-      if (globaltimer_ns() - t0 > TFOS_FLAG_TIMEOUT_NS) {
+      if (globaltimer_ns() - t0 > g_flag_timeout_ns) {
         printf("tfos: peer flag timeout (block %d, want %u, have %u)\n", blockIdx.x, target,
                ld_acquire_sys(p));
         __trap();
@@ -354,12 +357,30 @@ ps_push_dense_kernel(float* __restrict__ w_ps, const float* __restrict__ g, long
   }
 }
 
-// Sparse push (IndexedSlices): rows[idx[r]] += -lr * scale * grad_rows[r]
+// Sparse push (IndexedSlices): rows[idx[r]] += -lr * scale * grad_rows[r].  Rows whose width is
+// a multiple of 4 (every embedding table in practice) go 16 bytes at a time: one index
+// decomposition and one red.global.add.v4.f32 per four elements; duplicate indices simply add up.
 __global__ void __launch_bounds__(256)
 ps_push_sparse_kernel(float* __restrict__ w_ps, const float* __restrict__ g_rows,
                       const int* __restrict__ idx, int nrows, int width,
                       const float* __restrict__ hyper) {
   const float k = -hyper[0] * hyper[3];
+  const bool vec = (width & 3) == 0 &&
+                   ((reinterpret_cast<uintptr_t>(w_ps) | reinterpret_cast<uintptr_t>(g_rows)) & 15) == 0;
+  if (vec) {
+    const int w4 = width >> 2;
+    const long long total4 = static_cast<long long>(nrows) * w4;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total4;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+      const int r = static_cast<int>(i / w4), c = static_cast<int>(i - static_cast<long long>(r) * w4) * 4;
+      const float4 v = *reinterpret_cast<const float4*>(g_rows + static_cast<long long>(r) * width + c);
+      asm volatile("red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(
+                       w_ps + static_cast<long long>(idx[r]) * width + c),
+                   "f"(k * v.x), "f"(k * v.y), "f"(k * v.z), "f"(k * v.w)
+                   : "memory");
+    }
+    return;
+  }
   const long long total = static_cast<long long>(nrows) * width;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -539,6 +560,9 @@ cudaError_t allreduce_opt(const AllreduceOptArgs& a, int opt, int grid, cudaStre
     default: return cudaErrorInvalidValue;
   }
 }
+cudaError_t set_flag_timeout_ns(unsigned long long ns) {
+  return cudaMemcpyToSymbol(g_flag_timeout_ns, &ns, sizeof(ns));
+}
 cudaError_t bcast_pull(const BcastArgs& a, int grid, cudaStream_t s) {
   bcast_pull_kernel<<<grid, 512, 0, s>>>(a);
   return cudaGetLastError();
@@ -557,7 +581,7 @@ cudaError_t ps_push_dense(float* w_ps, const float* g, long long n, const float*
 }
 cudaError_t ps_push_sparse(float* w_ps, const float* g_rows, const int* idx, int nrows, int width,
                            const float* hyper, cudaStream_t s) {
-  long long blocks = (static_cast<long long>(nrows) * width + 255) / 256;
+  long long blocks = (static_cast<long long>(nrows) * width / ((width & 3) == 0 ? 4 : 1) + 255) / 256;
   if (blocks > 148 * 4) blocks = 148 * 4;
   if (blocks < 1) blocks = 1;
   ps_push_sparse_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(w_ps, g_rows, idx, nrows,

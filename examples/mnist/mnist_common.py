@@ -38,6 +38,9 @@ class Trainer(object):
 
   def step(self, images, labels):
     np, torch = self.np, self.torch
+    from tensorflowonspark_b200.utils import fault
+    self._steps = getattr(self, "_steps", 0) + 1
+    fault.maybe_inject(max(0, getattr(self.ctx, "rank", 0)), self._steps)   # TFOS_FAULT_INJECT
     if self.native:
       self.xh.copy_(torch.from_numpy(np.asarray(images, dtype=np.float32) / 255.0))
       self.yh.copy_(torch.from_numpy(np.asarray(labels, dtype=np.int32)))

@@ -73,6 +73,7 @@ def main_fun(argv, ctx):
   dev = torch.device("cuda", torch.cuda.current_device())
   comm = ctx.symmetric_comm() if world > 1 else None
   B = args.batch_size
+  from tensorflowonspark_b200.utils import fault
   net = resnet.CifarResNetTrainer(depth=args.resnet_size, batch=B, device=dev, comm=comm,
                                   lr=resnet.piecewise_lr(0, B * world))
   if comm is not None:
@@ -82,7 +83,7 @@ def main_fun(argv, ctx):
   if args.model_dir:
     start_step, state = checkpoint.load(ctx.absolute_path(args.model_dir))
     if state is not None:
-      net.store.load_state_dict(state["params"])
+      net.load_state_dict(state["params"])      # parameters + batch-norm running statistics
       net.optim.load_state_dict(state["optim"])
   synthetic = args.use_synthetic_data or not args.data_dir
   if synthetic:
@@ -113,6 +114,7 @@ def main_fun(argv, ctx):
       xh.copy_(torch.from_numpy(augment(images[idx], rng)))
       yh.copy_(torch.from_numpy(labels[idx].astype(np.int32)))
       net.set_input(xh, yh)
+    fault.maybe_inject(ctx.rank, step)      # TFOS_FAULT_INJECT (resilience tests), no-op otherwise
     loss = net.train_step()
     seen += B * world
     if (step + 1) % 100 == 0 or step + 1 == total:
@@ -125,11 +127,11 @@ def main_fun(argv, ctx):
     if args.model_dir and ctx.is_chief and (step + 1) % (steps_per_epoch * max(
         1, args.epochs_between_evals)) == 0:
       checkpoint.save(ctx.absolute_path(args.model_dir), step + 1,
-                      {"params": net.store.state_dict(), "optim": net.optim.state_dict()})
+                      {"params": net.state_dict(), "optim": net.optim.state_dict()})
   torch.cuda.synchronize()
   if args.model_dir and ctx.is_chief:
     checkpoint.save(ctx.absolute_path(args.model_dir), total,
-                    {"params": net.store.state_dict(), "optim": net.optim.state_dict()})
+                    {"params": net.state_dict(), "optim": net.optim.state_dict()})
 
 
 class LocalContext(object):

@@ -37,6 +37,7 @@ def main_fun(argv, ctx):
   from tensorflowonspark_b200.models import resnet
   from tensorflowonspark_b200.utils import checkpoint, metrics
   args = parse(argv[1:])
+  from tensorflowonspark_b200.utils import fault
   torch.cuda.set_device(0)  # the node runtime made the assigned GPU device 0
   comm = ctx.symmetric_comm() if ctx.world_size > 1 else None
   B = args.batch_size
@@ -54,7 +55,7 @@ def main_fun(argv, ctx):
   if args.model_dir:
     start, state = checkpoint.load(ctx.absolute_path(args.model_dir))
     if state is not None:
-      net.store.load_state_dict(state["params"])
+      net.load_state_dict(state["params"])      # parameters + batch-norm running statistics
       net.optim.load_state_dict(state["optim"])
       print("resumed from step", start)
   x, y = net.synthetic_batch(seed=ctx.rank)
@@ -68,6 +69,7 @@ def main_fun(argv, ctx):
   for step in range(start, start + args.train_steps):
     if args.epochs_per_step:
       net.set_lr(resnet.piecewise_lr(int(step * args.epochs_per_step), B * ctx.world_size))
+    fault.maybe_inject(ctx.rank, step)      # TFOS_FAULT_INJECT (resilience tests), no-op otherwise
     loss = net.train_step()
     if (step + 1) % 10 == 0:
       torch.cuda.synchronize()
@@ -80,7 +82,7 @@ def main_fun(argv, ctx):
       t0 = time.time()
     if args.model_dir and args.save_steps and (step + 1) % args.save_steps == 0 and ctx.is_chief:
       checkpoint.save(ctx.absolute_path(args.model_dir), step + 1,
-                      {"params": net.store.state_dict(), "optim": net.optim.state_dict()})
+                      {"params": net.state_dict(), "optim": net.optim.state_dict()})
   torch.cuda.synchronize()
 
 

@@ -35,6 +35,7 @@ def main_fun(args, ctx):
   import torch
   from tensorflowonspark_b200.feed import DevicePrefetcher
   from tensorflowonspark_b200.models import unet
+  from tensorflowonspark_b200.utils import fault
   torch.cuda.set_device(0)
   comm = ctx.symmetric_comm() if ctx.world_size > 1 else None
   B = args.batch_size
@@ -65,6 +66,7 @@ def main_fun(args, ctx):
       net.set_input(bx, by)
       pre.release()
       h3 = time.time()
+      fault.maybe_inject(ctx.rank, step)   # TFOS_FAULT_INJECT (resilience tests), no-op otherwise
       loss = net.train_step()
       h4 = time.time()
       for k, d in enumerate((h1 - h0, h2 - h1, h3 - h2, h4 - h3)):
@@ -90,6 +92,7 @@ def main_fun(args, ctx):
     net.train_step()
     net.capture()
     for step in range(args.steps):
+      fault.maybe_inject(ctx.rank, step)
       loss = net.train_step()
       if (step + 1) % 10 == 0 and ctx.is_chief:
         torch.cuda.synchronize()

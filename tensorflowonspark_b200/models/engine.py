@@ -212,6 +212,12 @@ class BatchNorm(object):
     else:
       self.sum, self.sumsq = z(), z()
     self.mean, self.invstd, self.scale, self.shift = z(), z(), z(), z()
+    # accumulators of the backward reduction when it is fused into the epilogue of the data
+    # gradient that produces this unit's dy (enable_fused_reduce): zeroed with the same memset
+    self.red_g = self.red_gx = None
+    self.fused_reduce = False
+    if arena is not None:
+      self.red_g, self.red_gx = arena.take(self.C), arena.take(self.C)
     if running is not None:
       self.running_mean, self.running_var = running.take(self.C)
     else:
@@ -224,12 +230,18 @@ class BatchNorm(object):
   def stats(self):
     return (self.sum, self.sumsq)
 
-  def forward(self, x_raw, y, residual=None, act=1, training=True, fused_stats=True):
+  def forward(self, x_raw, y, residual=None, act=1, training=True, fused_stats=True, rev=False):
+    """``rev``: walk the rows last-to-first.  The convolution that produced ``x_raw`` wrote its
+    tiles first-to-last, so the END of the tensor is what the 126 MB L2 still holds; the apply
+    kernel then finishes at the START of ``y``, which is where the next convolution begins."""
     count = x_raw.numel() // self.C
+    ops.C().bn_set_row_reverse(bool(rev))
     # a residual unit's ReLU mask depends on the sum, not on x alone: keep it as one bit per
     # element so that the backward pass does not have to re-read the whole bf16 output
     # (the buffer is never released: a captured CUDA graph may hold its address)
-    if training and residual is not None and act == 1:
+    if training and act == 1 and (residual is not None or getattr(self, "fused_reduce", False)):
+      # (a unit whose backward reduction is fused into a dgrad epilogue always keeps the bits:
+      # the epilogue and the apply kernel then read 1/16 of a byte per element for the mask)
       self.mask = self.ensure_mask(x_raw.numel(), x_raw.device)
     else:
       self.mask = None
@@ -257,7 +269,8 @@ class BatchNorm(object):
       buf = self._mask_buf = torch.empty(numel // 8, dtype=torch.uint8, device=device)
     return buf
 
-  def backward(self, dy, x_raw, y, dx, dres=None, relu=True, residual=False, mask=None):
+  def backward(self, dy, x_raw, y, dx, dres=None, relu=True, residual=False, mask=None,
+               rev=(False, False)):
     """relu mask: recomputed from x_raw with the forward scale/shift when the unit has no
     residual input (saves reading y: 2 of 6-8 bytes per element); from the stored y otherwise;
     ``mask``: another unit's bit mask (a projection shortcut's BN sees the gradient of the block
@@ -266,12 +279,26 @@ class BatchNorm(object):
     ysrc = y if mode == 1 else None
     if mask is not None and relu:
       mode, ysrc = 3, mask
-    elif mode == 1 and getattr(self, "mask", None) is not None:
+    elif relu and getattr(self, "mask", None) is not None:
       mode, ysrc = 3, self.mask   # bit mask written by forward(): 1/16 of y's bytes
+    if getattr(self, "fused_reduce", False):
+      # sum(g), sum(g x) were accumulated by the epilogue of the data gradient that wrote dy
+      # (ops/igemm.conv_dgrad(bn_reduce=...)): no reduction pass, the apply kernel finishes them
+      ops.C().bn_set_row_reverse(bool(rev[1]))
+      ops.K.bn_bwd_apply(dy, x_raw, ysrc, self.gamma, self.mean, self.invstd, self.dgamma,
+                         self.dbeta, dx, dres, mode, self.scale, self.shift, self.red_g,
+                         self.red_gx)
+      ops.C().bn_set_row_reverse(False)
+      return
+    # rev = (reduce, apply) row order: each kernel starts at the end where the previous one
+    # stopped, so that what it reads first is still in L2 (ResNetTrainer assigns the directions)
+    ops.C().bn_set_row_reverse(bool(rev[0]))
     ops.K.bn_bwd_reduce(dy, x_raw, ysrc, self.mean, self.invstd, self.dgamma, self.dbeta, mode,
                         self.scale, self.shift)
+    ops.C().bn_set_row_reverse(bool(rev[1]))
     ops.K.bn_bwd_apply(dy, x_raw, ysrc, self.gamma, self.mean, self.invstd, self.dgamma,
                        self.dbeta, dx, dres, mode, self.scale, self.shift)
+    ops.C().bn_set_row_reverse(False)
 
 
 class Conv(object):
@@ -290,7 +317,10 @@ class Conv(object):
             (W + 2 * self.pad - self.k) // self.stride + 1)
 
   def build(self, x, y, dy=None, dx=None, stats=None, relu=False, dx_accumulate=False,
-            need_dgrad=True, training=True, dx_acc_mask=None):
+            need_dgrad=True, training=True, dx_acc_mask=None, dx_bn_reduce=None):
+    """``dx_bn_reduce``: the BatchNorm whose dy this layer's data gradient produces (its input
+    has the shape of ``dx``): fuse that batch norm's backward reduction into the dgrad epilogue
+    when the plan allows it (every pixel of dx written by this launch)."""
     st = self.store
     self.x, self.y = x, y
     if not training:
@@ -304,8 +334,22 @@ class Conv(object):
     if training and dy is not None:
       self.wgrad = igemm.conv_wgrad(dy, x, st.g(self.sw), self.stride, self.pad)
       if need_dgrad and dx is not None:
-        self.dgrad = igemm.conv_dgrad(dy, st.w(self.sw), dx, self.stride, self.pad,
-                                      accumulate=dx_accumulate, acc_mask=dx_acc_mask)
+        red = None
+        if dx_bn_reduce is not None and dx_bn_reduce[0].red_g is not None:
+          bn_below, x_below, mask_below = dx_bn_reduce
+          red = (x_below, mask_below, bn_below.red_g, bn_below.red_gx)
+        try:
+          self.dgrad = igemm.conv_dgrad(dy, st.w(self.sw), dx, self.stride, self.pad,
+                                        accumulate=dx_accumulate, acc_mask=dx_acc_mask,
+                                        bn_reduce=red)
+          if red is not None:
+            dx_bn_reduce[0].fused_reduce = True
+        except (ValueError, RuntimeError) as e:
+          if red is None:
+            raise
+          # (a strided 1x1 does not write every pixel, odd channel counts leave ragged tiles)
+          self.dgrad = igemm.conv_dgrad(dy, st.w(self.sw), dx, self.stride, self.pad,
+                                        accumulate=dx_accumulate, acc_mask=dx_acc_mask)
     self.dy = dy
 
   def forward(self):

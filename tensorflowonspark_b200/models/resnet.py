@@ -102,6 +102,7 @@ class ResNetTrainer(object):
       self.p_stem_wgrad = igemm.stem_wgrad(self.g_stem_raw, self.xp, st.g(self.stem_w))
 
     x, H, W = self.pool, PH, PW
+    prev_block = None
     gx = _buf(x.shape, dev) if tr else None  # gradient wrt the block input
     self.g_pool = gx
     for b in self.blocks:
@@ -128,15 +129,29 @@ class ResNetTrainer(object):
       # the block output's ReLU mask (one bit per element, written by bn3's forward): identity
       # blocks fold "mask * dY" into conv1's accumulating dgrad instead of materialising it
       omask = b.u3.bn.ensure_mask(b.out.numel(), dev) if tr else None
+      # Fused batch-norm backward reductions (TFOS_BN_FUSED_REDUCE=0 disables): the data gradient
+      # that WRITES a batch norm's dy also accumulates that batch norm's sum(g), sum(g x):
+      #   conv3.dgrad -> g_a2 = dy of bn2        conv2.dgrad -> g_a1 = dy of bn1
+      #   identity block: conv1.dgrad (accumulating) completes g_x = dy of the PREVIOUS block's bn3
+      fr = tr and self.stats_arena is not None and os.environ.get("TFOS_BN_FUSED_REDUCE", "1") != "0"
+      red1 = (b.u1.bn, b.r1, b.u1.bn.ensure_mask(b.a1.numel(), dev)) if fr else None
+      red2 = (b.u2.bn, b.r2, b.u2.bn.ensure_mask(b.a2.numel(), dev)) if fr else None
+      redp = None
+      if fr and ident and prev_block is not None:
+        redp = (prev_block.u3.bn, prev_block.r3, prev_block.u3.bn.ensure_mask(
+            prev_block.out.numel(), dev))
       b.u1.conv.build(x, b.r1, b.g_r1, b.g_x, stats=b.u1.bn.stats, dx_accumulate=ident,
-                      training=tr, dx_acc_mask=omask if ident else None)
-      b.u2.conv.build(b.a1, b.r2, b.g_r2, b.g_a1, stats=b.u2.bn.stats, training=tr)
-      b.u3.conv.build(b.a2, b.r3, b.g_r3, b.g_a2, stats=b.u3.bn.stats, training=tr)
+                      training=tr, dx_acc_mask=omask if ident else None, dx_bn_reduce=redp)
+      b.u2.conv.build(b.a1, b.r2, b.g_r2, b.g_a1, stats=b.u2.bn.stats, training=tr,
+                      dx_bn_reduce=red1)
+      b.u3.conv.build(b.a2, b.r3, b.g_r3, b.g_a2, stats=b.u3.bn.stats, training=tr,
+                      dx_bn_reduce=red2)
       if b.ds is not None:
         b.rd, b.idn = _buf(b.r3.shape, dev), _buf(b.r3.shape, dev)
         b.g_rd = _buf(b.r3.shape, dev) if tr else None
         b.ds.conv.build(x, b.rd, b.g_rd, b.g_x, stats=b.ds.bn.stats, dx_accumulate=True,
                         training=tr)
+      prev_block = b
       x, H, W = b.out, H2, W2
       if tr:
         gx = b.g_out
@@ -170,6 +185,28 @@ class ResNetTrainer(object):
     self.graph = None
     self.mean = [0.485, 0.456, 0.406]
     self.std = [0.229, 0.224, 0.225]
+    self._assign_directions()
+
+  def _assign_directions(self):
+    """L2 hand-over ("serpentine") schedule, TFOS_L2_SERPENTINE=0 disables it.
+
+    Activations are 13 - 411 MB per tensor at batch 256, the L2 holds 126 MB: a kernel that walks
+    a tensor front to back leaves its TAIL in L2.  Every memory-bound kernel of the chain
+    therefore starts at the end where its predecessor stopped:
+      forward   conv (tiles ascending) -> BN apply (rows descending) -> next conv (ascending) ...
+      backward  BN reduce (d) -> BN apply (not d) -> the unit's dgrad (d) -> next unit (not d) ...
+    Only the ORDER in which tiles / rows are visited changes; results are identical."""
+    self.serpentine = self.device.type == "cuda" and os.environ.get("TFOS_L2_SERPENTINE", "1") == "1"
+    d = False
+    for b in reversed(self.blocks):
+      for u in (b.u3, b.u2, b.u1):
+        u.rev = (d, not d) if self.serpentine else (False, False)
+        if self.serpentine and u.conv.dgrad is not None:
+          u.conv.dgrad.set_reverse(d)
+        d = not d
+      if b.ds is not None:
+        b.ds.rev = (False, True) if self.serpentine else (False, False)
+    self.stem_rev = (d, not d) if self.serpentine else (False, False)
 
   def _comm_buckets(self):
     """Gradient buckets for overlapping the fused all-reduce with backward: (begin, end, tag)
@@ -251,20 +288,21 @@ class ResNetTrainer(object):
       self.stats_arena.zero()   # the fused conv epilogues accumulate from zero every pass
     K.decode_normalize(self.in_u8, self.xp, igemm.STEM_PAD, self.mean, self.std)
     (self.p_stem_remote if remote else self.p_stem).run()
+    rv = self.serpentine
     self.stem_bn.forward(self.stem_raw, self.stem_act, None, 1, training)
     K.maxpool_fwd(self.stem_act, self.pool, self.pool_idx, 3, 2, 1)
     for b in self.blocks:
       for u, raw, act in ((b.u1, b.r1, b.a1), (b.u2, b.r2, b.a2)):
         run(u.conv)
-        u.bn.forward(raw, act, None, 1, training)
+        u.bn.forward(raw, act, None, 1, training, rev=rv)
       run(b.u3.conv)
       if b.ds is not None:
         run(b.ds.conv)
-        b.ds.bn.forward(b.rd, b.idn, None, 0, training)
+        b.ds.bn.forward(b.rd, b.idn, None, 0, training, rev=rv)
         idn = b.idn
       else:
         idn = b.x
-      b.u3.bn.forward(b.r3, b.out, idn, 1, training)
+      b.u3.bn.forward(b.r3, b.out, idn, 1, training, rev=rv)
     K.avgpool_fwd(self.last, self.avg)
     run(self.fc)
 
@@ -291,19 +329,19 @@ class ResNetTrainer(object):
       b = self.blocks[bi]
       # out = relu(bn3(r3) + idn): the masked gradient goes to both branches; the mask is applied
       # where g_out is consumed (here, in conv1's accumulate epilogue, in the shortcut's BN)
-      b.u3.bn.backward(b.g_out, b.r3, b.out, b.g_r3, relu=True, residual=True)
+      b.u3.bn.backward(b.g_out, b.r3, b.out, b.g_r3, relu=True, residual=True, rev=b.u3.rev)
       b.u3.conv.backward()
-      b.u2.bn.backward(b.g_a2, b.r2, b.a2, b.g_r2, relu=True)
+      b.u2.bn.backward(b.g_a2, b.r2, b.a2, b.g_r2, relu=True, rev=b.u2.rev)
       b.u2.conv.backward()
-      b.u1.bn.backward(b.g_a1, b.r1, b.a1, b.g_r1, relu=True)
+      b.u1.bn.backward(b.g_a1, b.r1, b.a1, b.g_r1, relu=True, rev=b.u1.rev)
       b.u1.conv.backward()  # writes (ds) or accumulates (identity) into g_x
       if b.ds is not None:
-        b.ds.bn.backward(b.g_out, b.rd, None, b.g_rd, relu=True, mask=b.u3.bn.mask)
+        b.ds.bn.backward(b.g_out, b.rd, None, b.g_rd, relu=True, mask=b.u3.bn.mask, rev=b.ds.rev)
         b.ds.conv.backward()  # accumulates into g_x
       self.optim.launch(bi)   # buckets that became final start their all-reduce now
     K.maxpool_bwd(self.g_pool, self.pool_idx, self.g_stem_act, 3, 2, 1)
     self.stem_bn.backward(self.g_stem_act, self.stem_raw, self.stem_act, self.g_stem_raw,
-                          relu=True)
+                          relu=True, rev=self.stem_rev)
     self.p_stem_wgrad.run()
 
   # ------------------------------------------------------------------ API

@@ -57,6 +57,13 @@ class Plan(object):
   def num_launches(self):
     return len(self.handles)
 
+  def set_reverse(self, flag):
+    """Walk the pixel tiles last-to-first (forward-like plans): an L2 hand-over hint - start where
+    the kernel that produced this plan's input stopped writing (models/resnet.py)."""
+    C = _C()
+    for h in self.handles:
+      C.igemm_set_reverse(h, bool(flag))
+
   def info(self):
     return [_C().igemm_info(h) for h in self.handles]
 
@@ -211,13 +218,18 @@ def conv_fprop(x, w, y, stride=1, pad=0, bias=None, relu=False, stats=None):
 
 
 def conv_dgrad(dy, w, dx, stride=1, pad=0, accumulate=False, relu=False, bias=None, stats=None,
-               acc_mask=None):
+               acc_mask=None, bn_reduce=None):
   """dx[N,H,W,Cin] (=|+=) conv_transpose(dy[N,OH,OW,Cout], w[Cout,R,S,Cin]).
 
   Also the forward of a transposed convolution (Keras Conv2DTranspose) when
   ``w`` is laid out [Cin_of_the_transposed_conv, R, S, Cout_of_it].
   For stride 2 the output is split in four parity classes, each a small
   stride-1 convolution over dy with the taps of matching parity.
+
+  ``bn_reduce = (x_raw, mask_bits | None, sum_g, sum_gx)``: dx is the gradient entering the batch
+  norm whose input was ``x_raw`` (shape of dx); the epilogue accumulates the two per-channel sums
+  of that batch norm's backward reduction while it stores dx (csrc/igemm.h: red_x).  Requires
+  that this call writes EVERY pixel of dx (raises ValueError otherwise: a strided 1x1 does not).
   """
   N, OH, OW, Cout = dy.shape
   _, R, S, Cin = w.shape
@@ -232,6 +244,8 @@ def conv_dgrad(dy, w, dx, stride=1, pad=0, accumulate=False, relu=False, bias=No
             if (ph + pad - r) % stride == 0 and (pw + pad - s) % stride == 0]
     if not taps:
       assert accumulate, "strided dgrad class without taps needs accumulate=True (or a pre-zeroed dx)"
+      if bn_reduce is not None:
+        raise ValueError("fused BN reduction: this data gradient does not write every pixel")
       continue
     ch, cw = -(-(H - ph) // stride), -(-(W - pw) // stride)  # pixels of this class
     if ch <= 0 or cw <= 0:
@@ -252,9 +266,16 @@ def conv_dgrad(dy, w, dx, stride=1, pad=0, accumulate=False, relu=False, bias=No
         "bias": bias.data_ptr() if bias is not None else 0, "out": dx.data_ptr(),
     }
     _stats_args(g, stats)  # transposed-conv *forward* feeding a batch norm
+    if bn_reduce is not None:
+      rx, rmask, sum_g, sum_gx = bn_reduce
+      assert stats is None and tuple(rx.shape) == tuple(dx.shape) and Cin % bn == 0
+      g["red_x"] = rx.data_ptr()
+      g["red_mask"] = rmask.data_ptr() if rmask is not None else 0
+      g["col_sum"], g["col_sumsq"] = sum_g.data_ptr(), sum_gx.data_ptr()
     handles.append(_C().igemm_plan_fwd(ta, tb, g, bn, True))
-  return Plan(handles, (dy, w, dx, bias, stats, acc_mask), "dgrad {}x{} s{} {}->{} @{}x{}".format(
-      R, S, stride, Cout, Cin, H, W))
+  return Plan(handles, (dy, w, dx, bias, stats, acc_mask, bn_reduce),
+              "dgrad {}x{} s{} {}->{} @{}x{}{}".format(R, S, stride, Cout, Cin, H, W,
+                                                      " +bnred" if bn_reduce is not None else ""))
 
 
 def _wgrad_plan(dy, dy_whn, Cout, x, x_whn, Cin, dw, ldw, taps, mul, es, box=None, c_box_b=None,

@@ -43,6 +43,12 @@ class SymmComm(object):
     self._vmm = {}     # name -> (va, size, granularity) of VMM allocations
     self._pending = []
     self._fdsrv = None
+    # a rank that waits for a dead peer gives up after TFOS_FLAG_TIMEOUT_MS (default 20 s): the
+    # kernel traps, the CUDA error surfaces in the training loop and reaches the driver through
+    # the node's error queue instead of hanging the job
+    if self.device.type == "cuda" and os.environ.get("TFOS_FLAG_TIMEOUT_MS"):
+      with torch.cuda.device(self.device):
+        ops.C().set_flag_timeout_ms(float(os.environ["TFOS_FLAG_TIMEOUT_MS"]))
     self.nvls = self._probe_nvls()
     self.flags = self.alloc("__flags__", FLAG_SLOTS * 32, torch.int32)
     self.epochs = torch.zeros(FLAG_SLOTS, dtype=torch.int32, device=self.device)

@@ -11,6 +11,7 @@ output mappings keep their meaning.
 """
 import argparse
 import copy
+import os
 import logging
 import sys
 
@@ -375,12 +376,37 @@ def _apply_state(state, inputs):
   raise TypeError("export at hand has no builder: cannot run inference from a bare state dict")
 
 
+_single_node_gpus = None   # GPU set this python worker settled on (python-worker reuse)
+
+
 def single_node_env(args):
-  """Environment for a single-node process inside a Spark task (GPU slot, classpath)."""
+  """Environment for a single-node process inside a Spark task (GPU slot, classpath).
+
+  Order of preference for the GPU: what this python worker already uses (executors are reused
+  across partitions: the replica stays on its device) -> Spark's resource API (one address per
+  executor, no two executors on one GPU) -> ``gpu_info`` (reference behaviour, pipeline.py:
+  647-659 -> util.single_node_env: a random free GPU)."""
+  global _single_node_gpus
   if isinstance(args, list):
     sys.argv = args
   num_gpus = args.num_gpus if "num_gpus" in args else 1
+  if _single_node_gpus is not None:
+    os.environ["CUDA_VISIBLE_DEVICES"] = _single_node_gpus
+    return
+  try:
+    from . import TFSparkNode
+    if num_gpus > 0 and TFSparkNode._has_spark_resource_api():
+      res = TFSparkNode.TaskContext.get().resources()
+      if res and "gpu" in res:
+        addrs = [str(a) for a in res["gpu"].addresses][:num_gpus]
+        if addrs:
+          os.environ["CUDA_VISIBLE_DEVICES"] = _single_node_gpus = ",".join(addrs)
+          logger.info("Using gpu(s) from the Spark resource API: %s", _single_node_gpus)
+          return
+  except Exception as e:  # pragma: no cover - resource API absent
+    logger.debug("Spark resource API not usable: %s", e)
   util.single_node_env(num_gpus)
+  _single_node_gpus = os.environ.get("CUDA_VISIBLE_DEVICES", "")
 
 
 def get_meta_graph_def(saved_model_dir, tag_set):

@@ -854,6 +854,13 @@ def ps_kernels():
   ref2 = ref.clone()
   ref2[base:base + rows * width].view(rows, width).index_add_(0, idx, -gr)
   ok &= _report("ps v1 push_sparse (duplicate rows add up)", _rel(f32, ref2), 1e-5)
+  idx5 = torch.randint(0, 1000, (300,), device="cuda")      # odd row width: scalar reductions
+  gr5 = torch.randn(300, 5, device="cuda")
+  client.push_sparse(gr5, idx5, 5, base=3, lr=0.5)
+  client.pull(out_fp32=f32)
+  torch.cuda.synchronize()
+  ref2[3:3 + 1000 * 5].view(1000, 5).index_add_(0, idx5, -0.5 * gr5)
+  ok &= _report("ps v1 push_sparse width 5, unaligned base", _rel(f32, ref2), 1e-5)
   client.close()
 
   # ---- slot mode
@@ -905,6 +912,86 @@ def ps_kernels():
     for c in clients:
       c.close()
   srv.stop()
+  return ok
+
+
+@check
+def dgrad_bn_reduce():
+  """Data-gradient epilogue with the fused batch-norm backward reduction (csrc/igemm.h: red_x):
+  while it stores dx it must accumulate sum(g) and sum(g * x) per channel, g = the ROUNDED dx it
+  stored, masked by the ReLU bits - checked against the same sums taken from the stored tensor in
+  PyTorch fp32 (1x1, 3x3, strided 3x3, accumulate + accumulate-mask variants, 64..512 channels),
+  and bn_bwd_apply fed with the raw sums against the stand-alone reduce + apply pair."""
+  import torch
+  from tensorflowonspark_b200 import ops
+  from tensorflowonspark_b200.ops import igemm
+  K = ops.K
+  ok = True
+  cases = [(4, 14, 14, 256, 256, 1, 1, False), (4, 28, 28, 128, 128, 3, 1, False),
+           (2, 56, 56, 64, 64, 3, 1, False), (4, 28, 28, 256, 128, 3, 2, False),
+           (4, 14, 14, 1024, 256, 1, 1, True), (2, 7, 7, 2048, 512, 1, 1, True),
+           (3, 10, 10, 64, 256, 1, 1, True)]
+  for (N, H, W, Cin, Cout, k, stride, acc) in cases:
+    OH, OW = (H + 2 * (k // 2) - k) // stride + 1, (W + 2 * (k // 2) - k) // stride + 1
+    dy = torch.randn(N, OH, OW, Cout, device="cuda").bfloat16()
+    w = (torch.randn(Cout, k, k, Cin, device="cuda") * 0.05).bfloat16()
+    x_raw = (torch.randn(N, H, W, Cin, device="cuda") * 1.5 + 0.3).bfloat16()
+    bits = torch.randint(0, 256, (N * H * W * Cin // 8,), device="cuda", dtype=torch.uint8)
+    mask = ((bits.view(-1, 1).int() >> torch.arange(8, device="cuda").int()) & 1).reshape(
+        N, H, W, Cin).float()
+    sum_g, sum_gx = torch.zeros(Cin, device="cuda"), torch.zeros(Cin, device="cuda")
+    dx = torch.randn(N, H, W, Cin, device="cuda").bfloat16() if acc else torch.zeros(
+        N, H, W, Cin, device="cuda", dtype=torch.bfloat16)
+    dx0 = dx.clone()
+    amask_bits = torch.randint(0, 256, (N * H * W * Cin // 8,), device="cuda", dtype=torch.uint8) \
+        if acc else None
+    plan = igemm.conv_dgrad(dy, w, dx, stride, k // 2, accumulate=acc, acc_mask=amask_bits,
+                            bn_reduce=(x_raw, bits, sum_g, sum_gx))
+    assert "bnred" in plan.desc
+    plan.run()
+    torch.cuda.synchronize()
+    # the stored tensor itself must equal the un-fused plan's output bit for bit
+    dx_ref = dx0.clone()
+    igemm.conv_dgrad(dy, w, dx_ref, stride, k // 2, accumulate=acc, acc_mask=amask_bits).run()
+    torch.cuda.synchronize()
+    tag = "{}x{} s{} {}->{}{}".format(k, k, stride, Cout, Cin, " acc" if acc else "")
+    ok &= _report("bnred {}: dx unchanged by the fusion".format(tag),
+                  float((dx != dx_ref).sum()), 0.5)
+    g = dx.float() * mask
+    ok &= _report("bnred {}: sum g".format(tag), _rel(sum_g, g.sum((0, 1, 2))), 2e-4)
+    ok &= _report("bnred {}: sum g*x".format(tag), _rel(sum_gx, (g * x_raw.float()).sum((0, 1, 2))),
+                  2e-4)
+    # apply kernel finishing the sums == reduce + apply
+    C, P = Cin, N * H * W
+    gamma, z = torch.rand(C, device="cuda") + 0.5, lambda: torch.zeros(C, device="cuda")  # noqa: E731
+    mean, invstd = x_raw.float().mean((0, 1, 2)), 1.0 / torch.sqrt(
+        x_raw.float().var((0, 1, 2), unbiased=False) + 1e-5)
+    d1, b1, d2, b2 = z(), z(), z(), z()
+    o1, o2 = torch.empty_like(dx), torch.empty_like(dx)
+    K.bn_bwd_reduce(dx, x_raw, bits, mean, invstd, d1, b1, 3, None, None)
+    K.bn_bwd_apply(dx, x_raw, bits, gamma, mean, invstd, d1, b1, o1, None, 3, None, None)
+    K.bn_bwd_apply(dx, x_raw, bits, gamma, mean, invstd, d2, b2, o2, None, 3, None, None, sum_g,
+                   sum_gx)
+    torch.cuda.synchronize()
+    xhat = (x_raw.float() - mean) * invstd
+    dg_ref, db_ref = (g * xhat).sum((0, 1, 2)), g.sum((0, 1, 2))
+    ok &= _report("bnred {}: dgamma from raw sums".format(tag), _rel(d2, dg_ref), 2e-3)
+    ok &= _report("bnred {}: dbeta from raw sums".format(tag), _rel(b2, db_ref), 2e-4)
+    dx_bn = gamma * invstd * (g - db_ref / P - xhat * dg_ref / P)
+    ok &= _report("bnred {}: bn dx (fused sums)".format(tag), _rel(o2, dx_bn), 2e-2)
+    ok &= _report("bnred {}: bn dx (stand-alone reduce)".format(tag), _rel(o1, dx_bn), 2e-2)
+  # a strided 1x1 does not write every pixel: the plan builder must refuse (callers fall back)
+  try:
+    igemm.conv_dgrad(torch.zeros(2, 4, 4, 64, device="cuda", dtype=torch.bfloat16),
+                     torch.zeros(64, 1, 1, 64, device="cuda", dtype=torch.bfloat16),
+                     torch.zeros(2, 8, 8, 64, device="cuda", dtype=torch.bfloat16), 2, 0,
+                     accumulate=True, bn_reduce=(torch.zeros(2, 8, 8, 64, device="cuda",
+                                                             dtype=torch.bfloat16), None,
+                                                 torch.zeros(64, device="cuda"),
+                                                 torch.zeros(64, device="cuda")))
+    ok &= _report("bnred: strided 1x1 refused", 1.0, 0.5)
+  except ValueError:
+    ok &= _report("bnred: strided 1x1 refused", 0.0, 0.5)
   return ok
 
 
