@@ -194,6 +194,7 @@ py::dict plan_info(int64_t h) {
   d["bn"] = p->bn;
   d["grid"] = p->grid;
   d["total_work"] = p->total_work;
+  d["cta_group"] = p->cta_group;
   return d;
 }
 

@@ -44,11 +44,14 @@ constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kBlockM = 128;
 constexpr int kABytes = kBlockM * 128;  // 128 rows x 64 bf16
 
-template <int BN>
+// CG = 2: CTA pair (cta_group::2, see ptx.cuh): each CTA stages its own 128 A rows and HALF of the
+// B tile, the leader issues M = 256 MMAs - half the B bytes per MAC from shared memory and from
+// the L2 -> SM fabric, which is what bounds the 3x3 layers (profiles/ncu_l3c2_r1.txt).
+template <int BN, int CG = 1>
 struct FwdCfg {
-  static constexpr int kBBytes = BN * 128;
+  static constexpr int kBBytes = BN * 128 / CG;
   static constexpr int kStage = kABytes + kBBytes;
-  static constexpr int kStages = (BN <= 64) ? 8 : (BN <= 128 ? 6 : 4);
+  static constexpr int kStages = (BN <= 64) ? 8 : (BN <= 128 ? 6 : (CG == 2 ? 6 : 4));
   static constexpr int kTmemCols = 2 * BN;  // double-buffered fp32 accumulator
   static constexpr int kStatBytes = BN * 2 * 4;
   static constexpr int kOutStageBytes = kEpiWarps * 4096;  // per warp: 32 rows x 128 B
@@ -79,11 +82,28 @@ __device__ __forceinline__ void red_shared_add(float* p, float v) {
 //   8 (with 0 or 2) fused batch-norm backward reduction over the stored gradient tile.
 constexpr int kEpiPlain = 0, kEpiStats = 1, kEpiAccum = 2, kEpiGeneric = 4, kEpiBnRed = 8;
 
-template <int BN, bool B_MN, int EPI>
+template <int BN, bool B_MN, int EPI, int CG = 1>
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const FwdArgs a, const int total_tiles) {
-  using Cfg = FwdCfg<BN>;
+  using Cfg = FwdCfg<BN, CG>;
+  constexpr bool k2 = CG == 2;
+  // CTA pair: rank in the pair, the leader issues the MMAs; a "tile" is then a PAIR of pixel boxes
+  const uint32_t crank = k2 ? cluster_ctarank() : 0u;
+  const bool leader = crank == 0u;
+  const int tile0 = k2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int tstep = k2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int m_boxes = a.tiles_w * a.tiles_h * a.tiles_n;
+  // pixel box of (pair-)tile `tile` for this CTA; the odd tail box of a pair may lie outside the
+  // tensor: TMA then zero-fills and the epilogue finds no valid row
+  auto box_of = [&](int tile) {
+    int mt = tile / a.n_tiles;
+    if (k2) {
+      if (a.reverse) mt = (m_boxes + 1) / 2 - 1 - mt;
+      return 2 * mt + static_cast<int>(crank);
+    }
+    return a.reverse ? m_boxes - 1 - mt : mt;
+  };
   extern __shared__ __align__(1024) uint8_t smem[];
   float* stat_smem = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStage);
   uint8_t* out_stage = smem + Cfg::kStages * Cfg::kStage + Cfg::kStatBytes;
@@ -113,19 +133,26 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&tfull[i], 1);
       // 64-column tiles are one slab wide: the two warps of a lane quarter then take ALTERNATE
       // tiles (= alternate TMEM buffers) instead of one of them idling, see the epilogue
-      mbar_init(&tempty[i], (BN == 64 && a.n_tiles == 1) ? kEpiWarps / 2 : kEpiWarps);
+      mbar_init(&tempty[i], k2 ? 2 * kEpiWarps
+                                : ((BN == 64 && a.n_tiles == 1) ? kEpiWarps / 2 : kEpiWarps));
     }
     mbar_init(bfull, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    tmem_relinquish();
+    if (k2) {   // both CTAs of the pair allocate (same columns in both TMEMs)
+      tmem_alloc_2cta(tmem_slot, Cfg::kTmemCols);
+      tmem_relinquish_2cta();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::kTmemCols);
+      tmem_relinquish();
+    }
   }
   if (threadIdx.x >= 64)
     for (int i = threadIdx.x - 64; i < BN * 2; i += kEpiThreads) stat_smem[i] = 0.f;
   tc_fence_before();
-  __syncthreads();
+  if (k2) cluster_sync_all();   // the peer's barriers and TMEM exist before anyone signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -139,6 +166,7 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t stage_tx =
       stem ? kStemStage
            : static_cast<uint32_t>(rows) * 128u + (resident ? 0u : Cfg::kBBytes);
+  // (CTA pair: host guarantees !resident && !stem; the leader's barrier counts both CTAs' bytes)
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -146,7 +174,18 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       auto load_b = [&](uint8_t* sB, uint64_t* bar, int nt, int t, int kc) {
-        if (B_MN) {
+        if (k2) {   // this CTA's half of the B tile: columns / rows [crank * BN/2, +BN/2)
+          if (B_MN) {
+#pragma unroll
+            for (int j = 0; j < BN / 128; ++j)
+              tma_load_2d_2cta(sB + j * 8192, &tmB, bar,
+                               nt * BN + (static_cast<int>(crank) * (BN / 128) + j) * 64 + a.tap_bn[t],
+                               a.tap_bk[t] + kc * 64);
+          } else {
+            tma_load_2d_2cta(sB, &tmB, bar, a.tap_bk[t] + kc * 64,
+                             nt * BN + static_cast<int>(crank) * (BN / 2));
+          }
+        } else if (B_MN) {
 #pragma unroll
           for (int j = 0; j < BN / 64; ++j)
             tma_load_2d(sB + j * 8192, &tmB, bar, nt * BN + j * 64 + a.tap_bn[t],
@@ -155,19 +194,18 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tma_load_2d(sB, &tmB, bar, a.tap_bk[t] + kc * 64, nt * BN);
         }
       };
-      if (resident && blockIdx.x < total_tiles) {
+      if (resident && tile0 < total_tiles) {
         // the host picked a grid that is a multiple of n_tiles: this CTA's nt never changes
-        const int nt = blockIdx.x % a.n_tiles;
+        const int nt = tile0 % a.n_tiles;
         mbar_expect_tx(bfull, static_cast<uint32_t>(k_iters) * Cfg::kBBytes);
         for (int it = 0; it < k_iters; ++it) {
           const int t = it / a.k_chunks, kc = it - t * a.k_chunks;
           load_b(smem + it * Cfg::kBBytes, bfull, nt, t, kc);
         }
       }
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < total_tiles; tile += tstep) {
         const int nt = tile % a.n_tiles;
-        int mt = tile / a.n_tiles;
-        if (a.reverse) mt = a.tiles_w * a.tiles_h * a.tiles_n - 1 - mt;
+        int mt = box_of(tile);
         const int tw = mt % a.tiles_w;
         mt /= a.tiles_w;
         const int th = mt % a.tiles_h;
@@ -188,10 +226,19 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int t = it / a.k_chunks, kc = it - t * a.k_chunks;
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sA = ring + stage * stage_stride;
-          mbar_expect_tx(&full[stage], stage_tx);
-          tma_load_4d(sA, &tmA, &full[stage], kc * 64 + a.tap_dc[t], cw + a.tap_dw[t],
-                      ch + a.tap_dh[t], cn);
-          if (!resident) load_b(sA + kABytes, &full[stage], nt, t, kc);
+          if (k2) {
+            // only the leader arms the (leader's) barrier, with the bytes of BOTH CTAs; the
+            // peer's TMA completions are counted there too (barrier address, peer bit cleared)
+            if (leader) mbar_expect_tx(&full[stage], 2 * stage_tx);
+            tma_load_4d_2cta(sA, &tmA, &full[stage], kc * 64 + a.tap_dc[t], cw + a.tap_dw[t],
+                             ch + a.tap_dh[t], cn);
+            load_b(sA + kABytes, &full[stage], nt, t, kc);
+          } else {
+            mbar_expect_tx(&full[stage], stage_tx);
+            tma_load_4d(sA, &tmA, &full[stage], kc * 64 + a.tap_dc[t], cw + a.tap_dw[t],
+                        ch + a.tap_dh[t], cn);
+            if (!resident) load_b(sA + kABytes, &full[stage], nt, t, kc);
+          }
           if (++stage == nstages) {
             stage = 0;
             phase ^= 1;
@@ -201,14 +248,14 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BN, false, B_MN);
+    if (lane == 0 && (!k2 || leader)) {
+      constexpr uint32_t idesc = umma_idesc_bf16(k2 ? 2 * kBlockM : kBlockM, BN, false, B_MN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      if (resident && blockIdx.x < total_tiles) mbar_wait(bfull, 0);
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      if (resident && tile0 < total_tiles) mbar_wait(bfull, 0);
+      for (int tile = tile0; tile < total_tiles; tile += tstep) {
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -241,16 +288,23 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint64_t bd0 =
               B_MN ? umma_desc_sw128(b_base, 8192, 1024) : umma_desc_sw128(b_base, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(d_tmem, ad0 + k * 2, bd0 + k * (B_MN ? 128 : 2), idesc,
-                      (it | k) != 0 ? 1u : 0u);
-          umma_commit(&empty[stage]);
+          for (int k = 0; k < 4; ++k) {
+            if (k2)
+              umma_bf16_2cta(d_tmem, ad0 + k * 2, bd0 + k * (B_MN ? 128 : 2), idesc,
+                             (it | k) != 0 ? 1u : 0u);
+            else
+              umma_bf16(d_tmem, ad0 + k * 2, bd0 + k * (B_MN ? 128 : 2), idesc,
+                        (it | k) != 0 ? 1u : 0u);
+          }
+          if (k2) umma_commit_2cta(&empty[stage], 0x3);   // both producers may refill the stage
+          else umma_commit(&empty[stage]);
           if (++stage == nstages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull[acc]);
+        if (k2) umma_commit_2cta(&tfull[acc], 0x3);       // both epilogues may read their rows
+        else umma_commit(&tfull[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -349,14 +403,13 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       asm volatile("bar.sync 1, 256;" ::: "memory");
     };
     int it = -1;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < total_tiles; tile += tstep) {
       ++it;
       if (split && (it & 1) != half) continue;   // the other half-group owns this tile
       const int acc = it & 1;                    // TMEM buffer / barrier pair of this tile
       const uint32_t acc_phase = (it >> 1) & 1;
       const int nt = tile % a.n_tiles;
-      int mt = tile / a.n_tiles;
-      if (a.reverse) mt = a.tiles_w * a.tiles_h * a.tiles_n - 1 - mt;
+      int mt = box_of(tile);
       const int tw = mt % a.tiles_w;
       mt /= a.tiles_w;
       const int th = mt % a.tiles_h;
@@ -621,21 +674,29 @@ igemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
-      const int next_tile = tile + gridDim.x;
+      if (lane == 0) {
+        if (k2 && !leader) mbar_arrive_cluster(&tempty[acc], 0);   // the leader owns tempty
+        else mbar_arrive(&tempty[acc]);
+      }
+      const int next_tile = tile + tstep;
       if (!split && do_stats && (next_tile >= total_tiles || next_tile % a.n_tiles != nt))
         flush_stats(nt);
       if (!split && red_on && (next_tile >= total_tiles || next_tile % a.n_tiles != nt))
         flush_red(nt);
     }
     // split mode: the half-groups skip each other's tiles, so they meet only here (one n tile)
-    if (split && do_stats && blockIdx.x < total_tiles) flush_stats(0);
-    if (split && red_on && blockIdx.x < total_tiles) flush_red(0);
+    if (split && do_stats && tile0 < total_tiles) flush_stats(0);
+    if (split && red_on && tile0 < total_tiles) flush_red(0);
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  if (k2) {
+    cluster_sync_all();   // the peer's barriers / TMEM are signalled until both CTAs are done
+    if (warp == 1) tmem_dealloc_2cta(tmem_base, Cfg::kTmemCols);
+  } else {
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
 }
 
 // -------------------------------------------------------------- host side
@@ -690,18 +751,52 @@ bool encode(const TmapDesc& d, CUtensorMap* out, char* err, int errlen) {
 }
 
 template <int BN, bool B_MN, int EPI>
-cudaError_t launch_fwd_epi(const IGemmPlan* p, cudaStream_t s) {
+cudaError_t launch_fwd_epi1(const IGemmPlan* p, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_fwd_kernel<BN, B_MN, EPI>,
+    cudaError_t e = cudaFuncSetAttribute(igemm_fwd_kernel<BN, B_MN, EPI, 1>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          FwdCfg<BN>::kSmem);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  igemm_fwd_kernel<BN, B_MN, EPI><<<p->grid, kThreads, FwdCfg<BN>::kSmem, s>>>(
+  igemm_fwd_kernel<BN, B_MN, EPI, 1><<<p->grid, kThreads, FwdCfg<BN>::kSmem, s>>>(
       p->tmA, p->tmB, p->fa, p->total_work);
   return cudaGetLastError();
+}
+
+// CTA-pair variant: cluster (2,1,1) launch; only N = 256 tiles are built that way
+template <bool B_MN, int EPI>
+cudaError_t launch_fwd_epi2(const IGemmPlan* p, cudaStream_t s) {
+  auto kern = igemm_fwd_kernel<256, B_MN, EPI, 2>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         FwdCfg<256, 2>::kSmem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(p->grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = FwdCfg<256, 2>::kSmem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, p->tmA, p->tmB, p->fa, p->total_work);
+}
+
+template <int BN, bool B_MN, int EPI>
+cudaError_t launch_fwd_epi(const IGemmPlan* p, cudaStream_t s) {
+  if constexpr (BN == 256) {
+    if (p->cta_group == 2) return launch_fwd_epi2<B_MN, EPI>(p, s);
+  }
+  return launch_fwd_epi1<BN, B_MN, EPI>(p, s);
 }
 
 template <int BN, bool B_MN>
@@ -756,7 +851,28 @@ IGemmPlan* igemm_plan_fwd(const TmapDesc& a, const TmapDesc& b, const FwdArgs& a
   IGemmPlan* p = new (std::nothrow) IGemmPlan();
   if (!p) return nullptr;
   memset(p, 0, sizeof(*p));
-  if (!encode(a, &p->tmA, err, errlen) || !encode(b, &p->tmB, err, errlen)) {
+  // CTA pairs (cta_group::2) for N = 256 tiles that stream B: the 3x3 layers and the deep 1x1
+  // layers, which are bound by operand traffic (weight-stationary problems keep B resident in
+  // one CTA and gain nothing).  TFOS_IGEMM_2CTA=0 disables, =1 forces it wherever it is legal.
+  static const int mode_2cta = [] {
+    const char* e = getenv("TFOS_IGEMM_2CTA");
+    return e == nullptr ? 2 : atoi(e);   // 2 = automatic
+  }();
+  const int k_iters0 = args.num_taps * args.k_chunks;
+  const long long m_boxes = static_cast<long long>(args.tiles_w) * args.tiles_h * args.tiles_n;
+  const long long b_bytes0 = static_cast<long long>(k_iters0) * bn * 128;
+  const bool would_be_resident =
+      args.n_tiles <= 8 && args.n_tiles * m_boxes >= 2 * num_sms &&
+      b_bytes0 + kMinAStages * kABytes <= static_cast<long long>(FwdCfg<256>::kStages) * FwdCfg<256>::kStage;
+  const bool legal_2cta = bn == 256 && !args.stem && m_boxes >= 2 && args.n_valid % 256 == 0 &&
+                          (b_mn || true);
+  const bool want_2cta = mode_2cta == 1 ? legal_2cta
+                         : (mode_2cta == 2 ? (legal_2cta && !would_be_resident &&
+                                              args.n_tiles * ((m_boxes + 1) / 2) >= num_sms / 2)
+                                           : false);
+  TmapDesc b2 = b;
+  if (want_2cta && !b_mn) b2.box[1] = bn / 2;   // K-major B: each CTA loads half of the N rows
+  if (!encode(a, &p->tmA, err, errlen) || !encode(b2, &p->tmB, err, errlen)) {
     delete p;
     return nullptr;
   }
@@ -764,7 +880,20 @@ IGemmPlan* igemm_plan_fwd(const TmapDesc& a, const TmapDesc& b, const FwdArgs& a
   p->kind = 0;
   p->bn = bn;
   p->b_mn = b_mn;
+  p->cta_group = want_2cta ? 2 : 1;
   p->total_work = args.n_tiles * args.tiles_w * args.tiles_h * args.tiles_n;
+  if (want_2cta) {
+    const int pairs_avail = num_sms / 2;
+    p->total_work = args.n_tiles * static_cast<int>((m_boxes + 1) / 2);
+    int pairs = p->total_work < pairs_avail ? p->total_work : pairs_avail;
+    // pairs pinned to one n tile keep the fused statistics in registers (as for single CTAs)
+    if (args.n_tiles > 1 && args.n_tiles <= 8 && p->total_work >= 2 * pairs_avail)
+      pairs = pairs_avail - pairs_avail % args.n_tiles;
+    p->grid = 2 * pairs;
+    p->fa.b_resident = 0;
+    p->fa.a_stages = 0;
+    return p;
+  }
   p->grid = p->total_work < num_sms ? p->total_work : num_sms;
   // a grid that is a multiple of n_tiles pins every CTA to one n tile: the fused statistics
   // then stay in registers until the CTA is done, and the filter tile can stay resident

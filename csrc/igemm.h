@@ -99,6 +99,7 @@ struct IGemmPlan {
   int b_mn;  // fwd-like only: B is MN-major ([K rows, N cols])
   int grid;
   int total_work;
+  int cta_group;  // fwd-like only: 2 = CTA pairs (cluster launch, M = 256 per MMA), else 1
 };
 
 // Returns nullptr and fills err on failure.
