@@ -134,3 +134,60 @@ def test_fused_optimizer_shards_partition_every_bucket():
         assert lo == pos and lo <= hi <= e and (lo - b) % 8 == 0
         pos = hi
       assert pos == e
+
+
+def test_fdshare_hands_a_descriptor_to_another_process(tmp_path):
+  """parallel/fdshare.py: a descriptor registered by one process is received (SCM_RIGHTS) and is
+  usable in another - the transport of cuMem / multicast handles between ranks."""
+  import multiprocessing as mp
+  import os
+  from tensorflowonspark_b200.parallel import fdshare
+  path = tmp_path / "payload.bin"
+  path.write_bytes(b"nvls-handle-stand-in")
+  srv = fdshare.FdServer()
+  fd = os.open(str(path), os.O_RDONLY)
+  srv.register("mem:grads", fd)
+
+  def child(addr, q):
+    try:
+      got = fdshare.fetch_fd(addr, "mem:grads")
+      q.put(os.read(got, 64))
+      try:
+        fdshare.fetch_fd(addr, "no-such-key")
+        q.put(b"missing key did not raise")
+      except KeyError:
+        q.put(b"KeyError")
+    except Exception as e:  # pragma: no cover
+      q.put(repr(e).encode())
+
+  ctx = mp.get_context("fork")
+  q = ctx.Queue()
+  p = ctx.Process(target=child, args=(srv.address, q))
+  p.start()
+  assert q.get(timeout=30) == b"nvls-handle-stand-in"
+  assert q.get(timeout=30) == b"KeyError"
+  p.join(30)
+  srv.close()
+
+
+def test_cluster_launcher_dry_run_plans_the_same_verbs_as_spark_ec2():
+  """scripts/cluster_launch.py (counterpart of the reference's scripts/spark_ec2.py): the
+  command plan of every verb, without touching a host."""
+  import importlib.util
+  import os
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  spec = importlib.util.spec_from_file_location("cluster_launch", os.path.join(root, "scripts", "cluster_launch.py"))
+  mod = importlib.util.module_from_spec(spec)
+  spec.loader.exec_module(mod)
+  base = ["--hosts", "n0,n1", "--spark-home", "/opt/spark", "--dry-run"]
+  rc, r = mod.main(base + ["launch"])
+  flat = [" ".join(c) for c in r.log]
+  assert rc == 0 and sum("rsync" in c for c in flat) == 2
+  assert any("start-master.sh" in c and "n0" in c for c in flat)
+  assert sum("start-worker.sh" in c for c in flat) == 2 and all("spark://n0:7077" in c for c in flat if "start-worker" in c)
+  rc, r = mod.main(base + ["destroy"])
+  flat = [" ".join(c) for c in r.log]
+  assert any("stop-master.sh" in c for c in flat) and sum("rm -rf" in c for c in flat) == 2
+  assert mod.master_url(["a", "b"]) == "spark://a:7077"
+  for verb in ("stop", "start", "get-master", "reboot-slaves"):
+    assert mod.main(base + [verb])[0] == 0
