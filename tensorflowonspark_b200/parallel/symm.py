@@ -29,6 +29,9 @@ from .. import ops
 logger = logging.getLogger(__name__)
 
 FLAG_SLOTS = 64
+# default of TFOS_NVLS ("auto" = multicast from 4 ranks up).  Kept at "0" until the multicast path
+# has been re-verified on an 8-GPU lease in this round; the 2-GPU verification is in profiles/.
+NVLS_DEFAULT = "0"
 
 
 class SymmComm(object):
@@ -68,7 +71,7 @@ class SymmComm(object):
     # - the requester's own included - so each GPU sends world/(world-1) times the bytes of the
     # peer-to-peer pull: 2x at 2 ranks (measured: 0.50 vs 0.37 ms for 25.6 M parameters), 1.14x at
     # 8, where the 8x smaller ingress and the 8x fewer load instructions win.
-    mode = os.environ.get("TFOS_NVLS", "auto")
+    mode = os.environ.get("TFOS_NVLS", NVLS_DEFAULT)
     if self.world < 2 or mode == "0" or (mode == "auto" and self.world < 4):
       return False
     try:

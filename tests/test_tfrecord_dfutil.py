@@ -114,3 +114,34 @@ def test_schema_hint_overrides_inference(sc, spark, tmp_path):
   hinted = dfutil.loadTFRecords(sc, out, schema_hint="struct<single:array<int>>")
   assert dict(hinted.dtypes)["single"] == "array<int>"
   assert sorted(r.single for r in hinted.collect()) == [[7], [8]]
+
+
+def test_tfrecord_pipeline_interleave_shuffle_shard_batch(tmp_path):
+  """utils/data.TFRecordPipeline (the tf.data chain of reference mnist_tf_ds.py:41-50): every
+  record is seen once per epoch, shards are disjoint and complete (by file and, with fewer files
+  than shards, by record), batches have the requested shape."""
+  import numpy as np
+  from tensorflowonspark_b200 import tfrecord
+  from tensorflowonspark_b200.utils import data
+  ids = list(range(103))
+  for f in range(4):
+    recs = [tfrecord.encode_example({"id": ("int64", [i]), "x": ("float", [i * 0.5, 1.0])})
+            for i in ids[f::4]]
+    tfrecord.write_records(str(tmp_path / "part-r-{:05d}".format(f)), recs)
+
+  def parse(rec):
+    ex = tfrecord.decode_example(rec)
+    return np.int64(ex["id"][1][0]), np.asarray(ex["x"][1], dtype=np.float32)
+
+  pat = str(tmp_path / "part-*")
+  assert len(data.list_files(pat)) == 4 and data.list_files(str(tmp_path)) == data.list_files(pat)
+  seen = [int(i) for i, _ in data.TFRecordPipeline(pat, epochs=2, shuffle_buffer=16, seed=1).map(parse)]
+  assert sorted(seen) == sorted(ids * 2) and seen[:20] != sorted(seen)[:20]
+  for world in (2, 8):     # 8 > number of files: sharding falls back to records
+    parts = [sorted(int(i) for i, _ in data.TFRecordPipeline(pat, seed=0).shard(world, r).map(parse))
+             for r in range(world)]
+    assert sorted(sum(parts, [])) == ids and all(parts)
+  batches = list(data.TFRecordPipeline(pat, shuffle_buffer=8).map(parse).batch(10))
+  assert len(batches) == 10 and batches[0][0].shape == (10,) and batches[0][1].shape == (10, 2)
+  tail = list(data.TFRecordPipeline(pat).map(parse).batch(10, drop_remainder=False))
+  assert len(tail) == 11 and tail[-1][0].shape == (3,)
