@@ -6,8 +6,7 @@ mkdir -p gpurun_out
 run() { timeout 420 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $1 "${@:2}"; }
 TFOS_FULL=1 run 29601 tools/gpu_check_multi.py > gpurun_out/${tag}_multi.log 2>&1; grep "TIMING\|SUMMARY\|FAIL" gpurun_out/${tag}_multi.log | head -12
 run 29602 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/${tag}_ours.json 2> gpurun_out/${tag}_ours.err; tail -1 gpurun_out/${tag}_ours.json | cut -c1-2500
-TFOS_NVLS=0 TFOS_BENCH_COMM_DIAG=0 run 29603 bench.py --gpus $N --steps 20 --warmup 5 --no-e2e > gpurun_out/${tag}_ours_p2p.json 2> gpurun_out/${tag}_ours_p2p.err; tail -1 gpurun_out/${tag}_ours_p2p.json | cut -c1-400
-if [ "$N" != "8" ]; then TFOS_NVLS=1 TFOS_BENCH_COMM_DIAG=0 run 29604 bench.py --gpus $N --steps 20 --warmup 5 --no-e2e > gpurun_out/${tag}_ours_nvls.json 2> gpurun_out/${tag}_ours_nvls.err; tail -1 gpurun_out/${tag}_ours_nvls.json | cut -c1-400; fi
+TFOS_NVLS=1 run 29604 bench.py --gpus $N --steps 20 --warmup 5 --no-e2e > gpurun_out/${tag}_ours_nvls.json 2> gpurun_out/${tag}_ours_nvls.err; tail -1 gpurun_out/${tag}_ours_nvls.json | cut -c1-2500
 run 29605 bench.py --impl nccl-cudnn --gpus $N --steps 20 --warmup 5 > gpurun_out/${tag}_base.json 2> gpurun_out/${tag}_base.err; tail -1 gpurun_out/${tag}_base.json | cut -c1-1200
 if [ "$N" = "8" ]; then
 timeout 500 python bench.py --config ps --gpus 8 --steps 20 > gpurun_out/${tag}_ps.json 2> gpurun_out/${tag}_ps.err; tail -1 gpurun_out/${tag}_ps.json | cut -c1-1500
