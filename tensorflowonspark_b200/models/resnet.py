@@ -211,18 +211,22 @@ class ResNetTrainer(object):
   def _comm_buckets(self):
     """Gradient buckets for overlapping the fused all-reduce with backward: (begin, end, tag)
     where tag is the index of the block after whose backward the range is final ('stem' = end
-    of backward).  layer4+fc hold 2/3 of the parameters and are final a third into backward."""
+    of backward).  layer4+fc hold 2/3 of the parameters and are final a third into backward;
+    what is left for the un-overlappable tail after the stem's weight gradient is only stem +
+    layer1 (0.23 M of 25.6 M parameters) and the batch-norm parameters of stem..layer2."""
     st = self.store
 
-    def first_offset(prefix):
-      return min(s["offset"] for s in st.order if s["decay"] and s["name"].startswith(prefix))
+    def first_offset(prefix, decay=True):
+      return min(s["offset"] for s in st.order if s["decay"] == decay and s["name"].startswith(prefix))
 
     def first_block(prefix):
       return next(i for i, b in enumerate(self.blocks) if b.name.startswith(prefix))
 
-    b3, b4 = first_offset("layer3."), first_offset("layer4.")
+    b2, b3, b4 = first_offset("layer2."), first_offset("layer3."), first_offset("layer4.")
+    nd3 = first_offset("layer3.", decay=False)   # non-decayed tail: BN scale/offset in layer order
     return [(b4, st.decay_end, first_block("layer4.")), (b3, b4, first_block("layer3.")),
-            (0, b3, "stem"), (st.decay_end, st.total, "stem")]
+            (nd3, st.total, first_block("layer3.")), (b2, b3, first_block("layer2.")),
+            (0, b2, "stem"), (st.decay_end, nd3, "stem")]
 
   @staticmethod
   def _stem_init(shape, gen):

@@ -191,3 +191,43 @@ def test_cluster_launcher_dry_run_plans_the_same_verbs_as_spark_ec2():
   assert mod.master_url(["a", "b"]) == "spark://a:7077"
   for verb in ("stop", "start", "get-master", "reboot-slaves"):
     assert mod.main(base + [verb])[0] == 0
+
+
+def test_resnet50_comm_buckets_tile_the_parameter_vector():
+  """ResNetTrainer._comm_buckets (overlap of the fused all-reduce with backward): 8-aligned,
+  disjoint, covering [0, total); the un-overlappable tail is stem + layer1 only."""
+  import torch
+  from tensorflowonspark_b200.models import resnet
+  from tensorflowonspark_b200.models.engine import BatchNorm, Dense, ParamStore, normal
+  from tensorflowonspark_b200.models.resnet import _Block, _Unit
+
+  class Shell(resnet.ResNetTrainer):
+    def __init__(self):
+      pass
+
+  t, st = Shell(), ParamStore()
+  t.store, t.blocks = st, []
+  st.register("stem.conv.w", (64, 7, 64), True, None)
+  BatchNorm(st, "stem.bn", 64)
+  cin = 64
+  for si, nblocks in enumerate((3, 4, 6, 3)):
+    width = 64 * 2 ** si
+    for bi in range(nblocks):
+      b, name = _Block(), "layer{}.{}".format(si + 1, bi)
+      b.u1, b.u2 = _Unit(st, name + ".u1", cin, width, 1, 1), _Unit(st, name + ".u2", width, width, 3, 1)
+      b.u3 = _Unit(st, name + ".u3", width, width * 4, 1, 1)
+      b.ds = _Unit(st, name + ".ds", cin, width * 4, 1, 1) if bi == 0 else None
+      b.name = name
+      t.blocks.append(b)
+      cin = width * 4
+  Dense(st, "fc", cin, 1000, bias=True, init=normal(0.01))
+  for s in st._specs:
+    s["init"] = lambda shape, gen: torch.zeros(shape)
+  st.finalize(torch.device("cpu"))
+  buckets = t._comm_buckets()
+  cov = sorted((b, e) for b, e, _ in buckets)
+  assert all(b % 8 == 0 and e % 8 == 0 for b, e in cov)
+  assert cov[0][0] == 0 and cov[-1][1] == st.total
+  assert all(cov[i][1] == cov[i + 1][0] for i in range(len(cov) - 1))
+  tail = sum(e - b for b, e, tag in buckets if tag == "stem")
+  assert tail < 0.011 * st.total, tail      # ~1 % of the parameters are left for the tail
