@@ -91,6 +91,8 @@ def main_fun(args, ctx):
     net.set_input(x, (x[..., 0] > 127).int() + (x[..., 1] > 200).int())
     net.train_step()
     net.capture()
+    torch.cuda.synchronize()
+    t0 = time.time()          # steady-state rate: the clock starts after the capture
     for step in range(args.steps):
       fault.maybe_inject(ctx.rank, step)
       loss = net.train_step()

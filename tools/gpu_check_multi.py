@@ -83,8 +83,12 @@ def main():
     aux = comm.alloc("a%d" % vi, N - decay_end, torch.float32, multicast=nvls)
     grads.copy_(g_local)
     master = w0.clone()
-    s1, s2 = torch.zeros(N, device=dev), torch.zeros(N, device=dev)
-    hyper = torch.tensor([0.1, 0.9, 1e-2, 1.0 / world, 0.9, 0.999, 1e-7, 1.0], device=dev)
+    # Adam is checked in a well-conditioned state (v = 1, step 10): on the very first step the
+    # update is lr * g / |g|, so an element whose 8 gradients nearly cancel flips sign with the
+    # summation order and no two correct implementations agree
+    s1, s2 = torch.zeros(N, device=dev), torch.full((N,), 1.0 if opt == 2 else 0.0, device=dev)
+    hyper = torch.tensor([0.1, 0.9, 1e-2, 1.0 / world, 0.9, 0.999, 1e-7, 10.0 if opt == 2 else 1.0],
+                         device=dev)
     d = {"master": master.data_ptr(), "state1": s1.data_ptr(), "state2": s2.data_ptr(),
          "hyper": hyper.data_ptr(), "begin": 0, "end": N, "decay_end": decay_end, "world": world,
          "rank": rank, "slot": vi, "opt": opt, "grid": 64,
@@ -105,18 +109,20 @@ def main():
     g /= world
     g[:decay_end] += 1e-2 * w0[:decay_end]
     if opt == 2:
-      m, v = 0.1 * g, 0.001 * g * g
-      ref = w0 - 0.1 * (m / 0.1) / (torch.sqrt(v / 0.001) + 1e-7)
+      m, v = 0.1 * g, 0.999 + 0.001 * g * g
+      c1, c2 = 1.0 - 0.9 ** 10, 1.0 - 0.999 ** 10
+      ref = w0 - 0.1 * (m / c1) / (torch.sqrt(v / c2) + 1e-7)
     else:
       ref = w0 - 0.1 * g
     report("allreduce_{} bf16 weights (all shards)".format(name), rel(weights, ref), 1e-2)
-    report("allreduce_{} fp32 aux replica".format(name), rel(aux, ref[decay_end:]), 1e-5)
+    report("allreduce_{} fp32 aux replica".format(name), rel(aux, ref[decay_end:]),
+           1e-4 if opt == 2 else 1e-5)
     chunk = ((N + world - 1) // world + 7) // 8 * 8
     lo, hi = min(N, chunk * rank), min(N, chunk * (rank + 1))
     # Adam divides by sqrt(v): the order in which 8 peers' gradients are summed shows up at a
     # few 1e-4 on elements whose gradient nearly cancels (plus __powf under --use_fast_math)
     report("allreduce_{} master shard".format(name), rel(master[lo:hi], ref[lo:hi]),
-           1e-3 if opt == 2 else 1e-5)
+           1e-4 if opt == 2 else 1e-5)   # (__powf under --use_fast_math in the bias correction)
     # timing (momentum only): device-timed, max over ranks
     if opt == 1:
       grads.copy_(g_local)
