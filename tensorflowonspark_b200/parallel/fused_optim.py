@@ -46,6 +46,9 @@ class FusedOptimizer(object):
     self.state1 = _state("state1") if self.opt != 0 else None
     self.state2 = _state("state2") if self.opt == 2 else None
     self.step_count = 0
+    import os
+    env_grid = int(os.environ.get("TFOS_AR_GRID", "0"))   # CTAs of the fused kernel (experiments)
+    grid = grid or env_grid or None
     self.grid = grid or (148 if self.world == 1 else 64)
     n = store.total
     if not buckets:
