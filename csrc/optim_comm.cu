@@ -114,9 +114,9 @@ __global__ void __launch_bounds__(512, 1) allreduce_opt_kernel(const AllreduceOp
   const long long lo = a.begin + min(n, chunk * rank);
   const long long hi = a.begin + min(n, chunk * (rank + 1));
 
-  // NVLS: a thread keeps kU x 2 multimem.ld_reduce (32 bytes each, reduced in the switch) in
+  // NVLS: a thread keeps kU x 2 = 16 multimem.ld_reduce (16 bytes each, reduced in the switch) in
   // flight; the peer-to-peer path already has 2 x world loads per element group in flight
-  constexpr int kU = MULTIMEM ? 4 : 1;
+  constexpr int kU = MULTIMEM ? 8 : 1;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * 8;
   for (long long i0 = lo + (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
        i0 < hi; i0 += stride * kU) {
