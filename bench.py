@@ -230,11 +230,21 @@ def main():
   net = resnet.ResNetTrainer(depth=50, batch=B, image=args.image, num_classes=1000, device=dev,
                              lr=0.1 * B * world / 256.0, momentum=0.9, weight_decay=1e-4,
                              comm=comm)
-  if comm is not None:
-    comm.broadcast("weights", root=0)  # chief's initial variables win (startup broadcast)
-    comm.broadcast("aux32", root=0)
   x, y = net.synthetic_batch(seed=rank)
   net.set_input(x, y)
+  if comm is not None:
+    # startup: the chief's initial variables win.  The broadcast is FUSED with the first training
+    # step (TFOS_FUSED_BCAST=0: plain pull): the first forward pass reads its filters by TMA
+    # straight out of the root's peer-mapped weight buffer while the local copy fills on a side
+    # stream (ResNetTrainer.first_step_fused_broadcast; untimed warm-up work)
+    if os.environ.get("TFOS_FUSED_BCAST", "1") == "1":
+      net.bind_broadcast_root(0)
+      torch.cuda.synchronize(dev)
+      dist.barrier()
+      net.first_step_fused_broadcast()
+    else:
+      comm.broadcast("weights", root=0)
+      comm.broadcast("aux32", root=0)
 
   def sync_all():
     torch.cuda.synchronize(dev)
