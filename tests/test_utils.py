@@ -184,7 +184,8 @@ def test_cluster_launcher_dry_run_plans_the_same_verbs_as_spark_ec2():
   flat = [" ".join(c) for c in r.log]
   assert rc == 0 and sum("rsync" in c for c in flat) == 2
   assert any("start-master.sh" in c and "n0" in c for c in flat)
-  assert sum("start-worker.sh" in c for c in flat) == 2 and all("spark://n0:7077" in c for c in flat if "start-worker" in c)
+  assert sum("start-worker.sh" in c for c in flat) == 2
+  assert all("spark://n0:7077" in c for c in flat if "start-worker" in c)
   rc, r = mod.main(base + ["destroy"])
   flat = [" ".join(c) for c in r.log]
   assert any("stop-master.sh" in c for c in flat) and sum("rm -rf" in c for c in flat) == 2
