@@ -45,6 +45,42 @@ def export_model(export_dir):
   checkpoint.export_model(net, export_dir)
 
 
+def replica_probe(export_dir, batch, iters=20):
+  """Inside one executor: what the served replica sustains (a) fed with row cells (staging copy +
+  H2D + forward + read-back, no Spark row plumbing) and (b) with the staging buffer left as it is
+  (H2D + forward + read-back only) - the two numbers that say what bounds the TFModel path."""
+  import time as _t
+  import numpy as np
+  import torch
+  from tensorflowonspark_b200.models import resnet
+  from tensorflowonspark_b200.utils import checkpoint
+  state = torch.load(os.path.join(export_dir, "weights.pt"), map_location="cpu", weights_only=False)
+  m = resnet.ServedResNet(state, depth=50, image=IMG, num_classes=1000, batch=batch)
+  rows = [r[0] for r in gen_rows(batch, 7)]
+  out = {}
+  for name in ("rows", "gpu_only"):
+    for phase in ("warm", "timed"):
+      n = 4 if phase == "warm" else iters
+      torch.cuda.synchronize()
+      t0 = _t.perf_counter()
+      for _ in range(n):
+        if name == "rows":
+          m.submit_rows({"image": rows})
+        else:
+          m.feeder.acquire_host()
+          m.feeder.push_host()
+          m._enqueue(batch)
+        if m.pending() > 1:
+          m.collect()
+      while m.pending():
+        m.collect()
+      torch.cuda.synchronize()
+      dt = _t.perf_counter() - t0
+    out[name] = batch * iters / dt
+  del m
+  return [out]
+
+
 def run(gpus, batch=256, batches=40, warm_batches=4):
   import tempfile
   from tensorflowonspark_b200._spark import SparkConf, SparkContext, SparkSession
@@ -77,6 +113,8 @@ def run(gpus, batch=256, batches=40, warm_batches=4):
   t0 = time.perf_counter()
   rows = model.transform(frame(batch * batches)).collect()
   dt = time.perf_counter() - t0
+  probe = sc.parallelize(range(gpus), gpus).mapPartitions(
+      lambda it: replica_probe(export_dir, batch)).collect()
   sc.stop()
   n = len(rows)
   assert n == gpus * batch * batches and n_warm == gpus * batch * warm_batches
@@ -96,6 +134,12 @@ def run(gpus, batch=256, batches=40, warm_batches=4):
               "d2h_bytes_per_step": batch * (1000 * 4 + 8),
               "note": "same measurement: the public API is the only path"},
       "gpu_launches": None,
+      "replica_probe_images_per_s_per_gpu": {
+          "fed_with_row_cells (staging copy + H2D + forward + read-back)":
+              min(p["rows"] for p in probe),
+          "staging_untouched (H2D + forward + read-back)": min(p["gpu_only"] for p in probe),
+          "note": "in-executor rates of models/resnet.ServedResNet without Spark row plumbing: "
+                  "what is left of the gap to `value` / n_gpus is Python row handling"},
   }
 
 

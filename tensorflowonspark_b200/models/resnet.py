@@ -386,6 +386,73 @@ class ResNetTrainer(object):
     self._forward(False)
     return self.logits
 
+  # ------------------------------------------ inference with folded batch norm
+  def build_folded_inference(self):
+    """Serving path: every batch norm is folded into the convolution in front of it
+    (w' = w * gamma / sqrt(var + eps) per output channel, bias = beta - mean * that scale, from
+    the fp32 masters and the running statistics), ReLU and the residual add run in the conv
+    epilogues (bias / ReLU / accumulate), identity blocks accumulate IN PLACE into their input.
+    The forward pass is then 53 tcgen05 convolutions + 2 pools + the dense head: none of the 53
+    batch-norm passes (2/3 of the inference-time HBM traffic) remains.  Call again after the
+    parameters or running statistics change (``fold_batch_norms``)."""
+    assert not self.training, "folded inference is built on a training=False trainer"
+    st, dev = self.store, self.device
+    units = [("stem", self.stem_w, self.stem_bn)]
+    for b in self.blocks:
+      for u in (b.u1, b.u2, b.u3) + ((b.ds,) if b.ds is not None else ()):
+        units.append((u, u.conv.sw, u.bn))
+    self._fold_units = units
+    self.wf = torch.zeros_like(st.weights)        # folded bf16 filters, same layout as weights
+    self.bf = torch.zeros(sum((bn.C + 7) // 8 * 8 for _, _, bn in units), dtype=torch.float32,
+                          device=dev)
+    bias, off = {}, 0
+    for key, _, bn in units:
+      bias[id(bn)] = self.bf[off:off + bn.C]
+      off += (bn.C + 7) // 8 * 8
+    wv = lambda spec: st._view(self.wf, spec)  # noqa: E731
+    plans = [igemm.stem_fprop(self.xp, wv(self.stem_w), self.stem_act, bias=bias[id(self.stem_bn)],
+                              relu=True)]
+    cur = self.pool
+    for b in self.blocks:
+      s_ = b.stride
+      plans.append(igemm.conv_fprop(cur, wv(b.u1.conv.sw), b.a1, 1, 0, bias=bias[id(b.u1.bn)],
+                                    relu=True))
+      plans.append(igemm.conv_fprop(b.a1, wv(b.u2.conv.sw), b.a2, s_, 1, bias=bias[id(b.u2.bn)],
+                                    relu=True))
+      if b.ds is not None:
+        plans.append(igemm.conv_fprop(cur, wv(b.ds.conv.sw), b.out, s_, 0,
+                                      bias=bias[id(b.ds.bn)]))
+        target = b.out
+      else:
+        target = cur          # out = relu(conv3 + x): accumulate into x itself
+      plans.append(igemm.conv_fprop(b.a2, wv(b.u3.conv.sw), target, 1, 0, bias=bias[id(b.u3.bn)],
+                                    relu=True, accumulate=True))
+      cur = target
+    self._f_plans, self._f_last = plans, cur
+    self.fold_batch_norms()
+
+  def fold_batch_norms(self):
+    st = self.store
+    off = 0
+    for key, spec, bn in self._fold_units:
+      scale = st.m(bn.sg) * torch.rsqrt(bn.running_var + bn.eps)
+      w = st.m(spec).float()
+      st._view(self.wf, spec).copy_(w * scale.view(-1, *([1] * (w.dim() - 1))))
+      self.bf[off:off + bn.C].copy_(st.m(bn.sb) - bn.running_mean * scale)
+      off += (bn.C + 7) // 8 * 8
+
+  def forward_folded(self):
+    """logits of the staged batch through the folded network (capturable)."""
+    K = ops.K
+    K.decode_normalize(self.in_u8, self.xp, igemm.STEM_PAD, self.mean, self.std)
+    self._f_plans[0].run()
+    K.maxpool_fwd(self.stem_act, self.pool, self.pool_idx, 3, 2, 1)
+    for p in self._f_plans[1:]:
+      p.run()
+    K.avgpool_fwd(self._f_last, self.avg)
+    self.fc.forward()
+    return self.logits
+
   def set_lr(self, lr):
     self.optim.set_lr(lr)
 
@@ -427,6 +494,10 @@ class ServedResNet(object):
     self.net = ResNetTrainer(depth=depth, batch=batch, image=image, num_classes=num_classes,
                              device=device, training=False)
     self.net.load_state_dict(state)
+    self.folded = os.environ.get("TFOS_SERVE_FOLD_BN", "1") == "1"
+    if self.folded:
+      self.net.build_folded_inference()
+    self._fwd = self.net.forward_folded if self.folded else (lambda: self.net._forward(False))
     self.B, self.image, self.V = batch, image, num_classes
     dev = self.net.device
     self.feeder = DevicePrefetcher([((batch, image, image, 3), torch.uint8)], dev, depth=2)
@@ -436,6 +507,13 @@ class ServedResNet(object):
     self.done = [torch.cuda.Event() for _ in range(2)]
     self._pending = []
     self._k = 0
+    self.pred_dev = torch.zeros(batch, dtype=torch.int64, device=dev)
+    self.graph, self._batches = None, 0
+    self.use_graph = os.environ.get("TFOS_SERVE_GRAPH", "1") == "1"
+    self.copy_threads = max(1, int(os.environ.get("TFOS_SERVE_COPY_THREADS", "4")))
+    if self.copy_threads > 1:
+      from concurrent.futures import ThreadPoolExecutor
+      self._pool = ThreadPoolExecutor(max_workers=self.copy_threads, thread_name_prefix="tfos-stage")
 
   def submit(self, inputs):
     import numpy as np
@@ -462,23 +540,62 @@ class ServedResNet(object):
       raise ValueError("batch of {} rows exceeds the served batch size {}".format(n, self.B))
     (host,) = self.feeder.acquire_host()
     hv = host.numpy().reshape(self.B, -1)
-    for r, row in enumerate(rows):
-      hv[r] = np.frombuffer(row, dtype=np.uint8) if not isinstance(row, np.ndarray) \
-          else row.reshape(-1)
+
+    def fill(lo, hi):
+      for r in range(lo, hi):
+        row = rows[r]
+        hv[r] = np.frombuffer(row, dtype=np.uint8) if not isinstance(row, np.ndarray) \
+            else row.reshape(-1)
+
+    # 38.5 MB per 256-image batch: one thread copies ~5 GB/s, which is slower than the GPU
+    # consumes it (8.5 vs 6.5 ms per batch); numpy releases the GIL during the copies, so a few
+    # threads fill disjoint row ranges of the staging buffer in parallel
+    k = self.copy_threads
+    if k > 1 and n >= 4 * k:
+      step = (n + k - 1) // k
+      list(self._pool.map(lambda i: fill(i * step, min(n, (i + 1) * step)), range(k)))
+    else:
+      fill(0, n)
     if n < self.B:
       hv[n:] = 0
     self.feeder.push_host()
     self._enqueue(n)
 
+  def _capture(self):
+    """The whole forward pass (~165 launches) + arg-max as ONE CUDA graph: the host thread that
+    also fills the staging buffers spends microseconds, not a millisecond, per batch on launches."""
+    dev = self.net.device
+    cur = torch.cuda.current_stream(dev)
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+      self._fwd()
+      self.pred_dev.copy_(self.net.logits[:, :self.V].argmax(1))
+    cur.wait_stream(side)
+    torch.cuda.synchronize(dev)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+      self._fwd()
+      self.pred_dev.copy_(self.net.logits[:, :self.V].argmax(1))
+    self.graph = g
+
   def _enqueue(self, n):
     (dx,) = self.feeder.pop()
     self.net.set_input(dx)
     self.feeder.release()
-    logits = self.net.forward_only()
+    if self.graph is None and self.use_graph and self._batches >= 1:
+      self._capture()
+    if self.graph is not None:
+      self.graph.replay()
+    else:
+      self._fwd()
+      self.pred_dev.copy_(self.net.logits[:, :self.V].argmax(1))
+    self._batches += 1
+    logits = self.net.logits
     k = self._k
     self._k ^= 1
     self.h_logits[k].copy_(logits[:, :self.V], non_blocking=True)
-    self.h_pred[k].copy_(logits[:, :self.V].argmax(1), non_blocking=True)
+    self.h_pred[k].copy_(self.pred_dev, non_blocking=True)
     self.done[k].record(torch.cuda.current_stream(self.net.device))
     self._pending.append((k, n))
 

@@ -184,15 +184,17 @@ def gemm_wgrad(dy, x, dw):
 
 
 # --------------------------------------------------------------------- conv
-def conv_fprop(x, w, y, stride=1, pad=0, bias=None, relu=False, stats=None):
-  """y[N,OH,OW,Cout] = conv(x[N,H,W,Cin], w[Cout,R,S,Cin]) with fused bias/ReLU/BN statistics."""
+def conv_fprop(x, w, y, stride=1, pad=0, bias=None, relu=False, stats=None, accumulate=False):
+  """y[N,OH,OW,Cout] (=|+=) conv(x[N,H,W,Cin], w[Cout,R,S,Cin]) with fused bias/ReLU/BN statistics.
+  ``accumulate``: y = act(y + conv + bias) - the residual add of an inference network whose batch
+  norms are folded into the filters (models/resnet.py: build_folded_inference)."""
   N, H, W, Cin = x.shape
   Cout, R, S, _ = w.shape
   _, OH, OW, _ = y.shape
   assert Cin % 8 == 0 and w.shape[3] == Cin and R * S <= 9
   bn = _bn_for(Cout)
   if R == 1 and S == 1 and stride == 1 and pad == 0:
-    return gemm(x.view(-1, Cin), w.view(Cout, Cin), y.view(-1, Cout), "nk", bias, relu, False,
+    return gemm(x.view(-1, Cin), w.view(Cout, Cin), y.view(-1, Cout), "nk", bias, relu, accumulate,
                 stats)
   bw, bh, bnn, tw, th, tn = choose_box(OW, OH, N)
   if stride == 1:
@@ -208,7 +210,7 @@ def conv_fprop(x, w, y, stride=1, pad=0, bias=None, relu=False, stats=None):
       "tap_dw": [s - pad for (r, s) in taps], "tap_dh": [r - pad for (r, s) in taps],
       "tap_bk": [(r * S + s) * Cin for (r, s) in taps],
       "lim_w": OW, "lim_h": OH, "lim_n": N, "OW": OW, "OH": OH,
-      "ldo": Cout, "n_valid": Cout, "relu": int(relu),
+      "ldo": Cout, "n_valid": Cout, "relu": int(relu), "accumulate": int(accumulate),
       "bias": bias.data_ptr() if bias is not None else 0, "out": y.data_ptr(),
   }
   _stats_args(g, stats)

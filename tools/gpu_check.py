@@ -995,6 +995,75 @@ def dgrad_bn_reduce():
   return ok
 
 
+@check
+def folded_inference():
+  """Serving path with batch norm folded into the filters (ResNetTrainer.build_folded_inference:
+  bias / ReLU / in-place residual accumulate in the conv epilogues) against the un-folded
+  inference forward of the same parameters and running statistics, and against torchvision fp32
+  in eval mode."""
+  import torch
+  import torchvision
+  from tensorflowonspark_b200.models import resnet
+  from tensorflowonspark_b200.ops import igemm
+  ok = True
+  B, HW = 16, 224
+  net = resnet.ResNetTrainer(depth=50, batch=B, image=HW, device="cuda:0", training=False, seed=11)
+  gen = torch.Generator(device="cpu").manual_seed(5)
+  sd = net.state_dict()
+  for k in list(sd):
+    if k.endswith(".u3.bn.gamma"):
+      sd[k] = 0.2 + 0.2 * torch.rand(sd[k].shape, generator=gen)
+    elif k.endswith(".gamma"):
+      sd[k] = 0.8 + 0.4 * torch.rand(sd[k].shape, generator=gen)
+    elif k.endswith(".beta"):
+      sd[k] = 0.1 * torch.randn(sd[k].shape, generator=gen)
+  run = sd["__running__"].clone()
+  run.copy_(0.05 * torch.randn(run.shape, generator=gen))
+  sd["__running__"] = run
+  net.load_state_dict(sd)
+  # variances: make every batch norm's running variance a sane positive number
+  for b in [net.stem_bn] + [u.bn for blk in net.blocks for u in (blk.u1, blk.u2, blk.u3) +
+                            ((blk.ds,) if blk.ds is not None else ())]:
+    b.running_var.copy_(0.5 + torch.rand(b.C, generator=gen).to("cuda"))
+  x, _ = net.synthetic_batch(seed=2)
+  net.set_input(x)
+  ref_logits = net.forward_only().clone()
+  net.build_folded_inference()
+  out = net.forward_folded().clone()
+  torch.cuda.synchronize()
+  ok &= _report("folded vs un-folded inference logits", _rel_l2(out, ref_logits), 3e-2)
+  agree = float((out.argmax(1) == ref_logits.argmax(1)).float().mean())
+  ok &= _report("folded vs un-folded top-1 disagreement", 1.0 - agree, 0.13)
+  # torchvision fp32 eval with the same parameters / statistics
+  tv = torchvision.models.resnet50(weights=None).cuda().float().eval()
+  st = net.store
+  cv = lambda w: w.permute(0, 3, 1, 2).contiguous()  # noqa: E731
+
+  def put_bn(bn, m):
+    with torch.no_grad():
+      m.weight.copy_(st.f32(bn.sg)), m.bias.copy_(st.f32(bn.sb))
+      m.running_mean.copy_(bn.running_mean), m.running_var.copy_(bn.running_var)
+
+  with torch.no_grad():
+    tv.conv1.weight.copy_(cv(igemm.unpack_stem_weight(st.w(net.stem_w).float())))
+    put_bn(net.stem_bn, tv.bn1)
+    for blk in net.blocks:
+      si, bi = int(blk.name[5]) - 1, int(blk.name.split(".")[1])
+      t = getattr(tv, "layer{}".format(si + 1))[bi]
+      for u, c, m in ((blk.u1, t.conv1, t.bn1), (blk.u2, t.conv2, t.bn2), (blk.u3, t.conv3, t.bn3)):
+        c.weight.copy_(cv(st.w(u.conv.sw).float()))
+        put_bn(u.bn, m)
+      if blk.ds is not None:
+        t.downsample[0].weight.copy_(cv(st.w(blk.ds.conv.sw).float()))
+        put_bn(blk.ds.bn, t.downsample[1])
+    tv.fc.weight.copy_(st.w(net.fc.sw).float()), tv.fc.bias.copy_(st.f32(net.fc.sbias))
+    xin = net.xp[:, :, igemm.STEM_PAD:igemm.STEM_PAD + HW, :3].float().permute(0, 3, 1, 2).contiguous()
+    tv_logits = tv(xin)
+  ok &= _report("un-folded inference vs torchvision fp32 eval", _rel_l2(ref_logits, tv_logits), 3e-2)
+  ok &= _report("folded inference vs torchvision fp32 eval", _rel_l2(out, tv_logits), 4e-2)
+  return ok
+
+
 def main():
   names = sys.argv[1:]
   if names:
