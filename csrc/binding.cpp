@@ -293,6 +293,47 @@ void bn_bwd_apply(const Tensor& dy, const Tensor& x, c10::optional<Tensor> y, co
                            x.numel() / C, C, relu, optf(sum_g), optf(sum_gx), cur_stream()),
         "bn_bwd_apply");
 }
+void stem_bn_relu_pool_fwd(const Tensor& x, Tensor y, Tensor idx, const Tensor& sum,
+                           const Tensor& sumsq, const Tensor& gamma, const Tensor& beta,
+                           Tensor running_mean, Tensor running_var, Tensor mean, Tensor invstd,
+                           Tensor scale, Tensor shift, double count, double eps, double momentum) {
+  need(x, torch::kBFloat16, "x");
+  need(y, torch::kBFloat16, "y");
+  TORCH_CHECK(x.dim() == 4 && y.dim() == 4 && idx.numel() == y.numel(), "stem_bn_relu_pool_fwd: shapes");
+  tfos::BnFinalize f;
+  f.sum = sum.data_ptr<float>();
+  f.sumsq = sumsq.data_ptr<float>();
+  f.gamma = gamma.data_ptr<float>();
+  f.beta = beta.data_ptr<float>();
+  f.running_mean = running_mean.data_ptr<float>();
+  f.running_var = running_var.data_ptr<float>();
+  f.mean = mean.data_ptr<float>();
+  f.invstd = invstd.data_ptr<float>();
+  f.scale = scale.data_ptr<float>();
+  f.shift = shift.data_ptr<float>();
+  f.count = static_cast<float>(count);
+  f.eps = static_cast<float>(eps);
+  f.momentum = static_cast<float>(momentum);
+  check(tfos::stem_bn_relu_pool_fwd(x.data_ptr(), y.data_ptr(), idx.data_ptr<uint8_t>(), x.size(0),
+                                    x.size(1), x.size(2), x.size(3), y.size(1), y.size(2), f,
+                                    cur_stream()),
+        "stem_bn_relu_pool_fwd");
+}
+void stem_pool_bn_bwd(const Tensor& dy_pool, const Tensor& idx, const Tensor& x, const Tensor& gamma,
+                      const Tensor& mean, const Tensor& invstd, const Tensor& scale,
+                      const Tensor& shift, Tensor dgamma, Tensor dbeta, Tensor dx) {
+  need(dy_pool, torch::kBFloat16, "dy_pool");
+  need(x, torch::kBFloat16, "x");
+  need(dx, torch::kBFloat16, "dx");
+  TORCH_CHECK(x.dim() == 4 && dy_pool.dim() == 4 && dx.numel() == x.numel(), "stem_pool_bn_bwd: shapes");
+  check(tfos::stem_pool_bn_bwd(dy_pool.data_ptr(), idx.data_ptr<uint8_t>(), x.data_ptr(),
+                               gamma.data_ptr<float>(), mean.data_ptr<float>(),
+                               invstd.data_ptr<float>(), scale.data_ptr<float>(),
+                               shift.data_ptr<float>(), dgamma.data_ptr<float>(),
+                               dbeta.data_ptr<float>(), dx.data_ptr(), x.size(0), x.size(1),
+                               x.size(2), x.size(3), dy_pool.size(1), dy_pool.size(2), cur_stream()),
+        "stem_pool_bn_bwd");
+}
 void add_act(const Tensor& a, c10::optional<Tensor> b, Tensor out, int act) {
   need(a, torch::kBFloat16, "a");
   TORCH_CHECK(a.numel() % 8 == 0, "add_act: numel % 8");
@@ -624,6 +665,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("mean"), py::arg("invstd"), py::arg("dgamma"), py::arg("dbeta"), py::arg("dx"),
         py::arg("dres"), py::arg("relu"), py::arg("fscale"), py::arg("fshift"),
         py::arg("sum_g") = py::none(), py::arg("sum_gx") = py::none());
+  m.def("stem_bn_relu_pool_fwd", &stem_bn_relu_pool_fwd);
+  m.def("stem_pool_bn_bwd", &stem_pool_bn_bwd);
   m.def("add_act", &add_act);
   m.def("relu_bwd", &relu_bwd);
   m.def("colsum", &colsum);

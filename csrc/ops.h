@@ -115,6 +115,15 @@ cudaError_t ps_push_sparse(float* w_ps, const float* g_rows, const int* idx, int
                            const float* hyper, cudaStream_t s);
 cudaError_t ps_pull(const float* w_ps, float* w_local, void* w_bf16, long long n, cudaStream_t s);
 
+// fused tail of the ResNet stem (stem_fused.cu): BN + ReLU + 3x3/2 max pool forward; the max-pool
+// backward folded into the BN backward reduction + apply (two launches)
+cudaError_t stem_bn_relu_pool_fwd(const void* x, void* y, uint8_t* idx, int N, int H, int W, int C,
+                                  int OH, int OW, const BnFinalize& fin, cudaStream_t s);
+cudaError_t stem_pool_bn_bwd(const void* dy_pool, const uint8_t* idx, const void* x,
+                             const float* gamma, const float* mean, const float* invstd,
+                             const float* fscale, const float* fshift, float* dgamma, float* dbeta,
+                             void* dx, int N, int H, int W, int C, int OH, int OW, cudaStream_t s);
+
 // parameter server with resident optimizer state ("slot mode", parallel/ps.py)
 struct PsApplyArgs {          // server side, all pointers local to the PS GPU
   float* master;              // [n] fp32 parameters of this server's slice (+ non-trainable tail)

@@ -83,7 +83,7 @@ class ResNetTrainer(object):
     self.xp = _buf((B, image, Wp, 8), dev)
     self.labels = torch.zeros(B, dtype=torch.int32, device=dev)
     self.stem_raw = _buf((B, OH, OW, 64), dev)
-    self.stem_act = _buf((B, OH, OW, 64), dev)
+    self.stem_act = None   # allocated below unless the fused stem tail makes it unnecessary
     PH, PW = (OH + 2 - 3) // 2 + 1, (OW + 2 - 3) // 2 + 1
     self.pool = _buf((B, PH, PW, 64), dev)
     self.pool_idx = _buf((B, PH, PW, 64), dev, torch.uint8)
@@ -94,10 +94,14 @@ class ResNetTrainer(object):
         "TFOS_BN_FUSED_FINALIZE", "1") != "0") else None
     self.running = engine.RunningArena(dev)   # all BN running statistics, one flat buffer
     self.stem_bn.build(dev, self.stats_arena, self.running)
+    self.fuse_stem = (tr and self.stats_arena is not None and dev.type == "cuda"
+                      and os.environ.get("TFOS_FUSE_STEM", "1") != "0")
+    if not self.fuse_stem:
+      self.stem_act = _buf((B, OH, OW, 64), dev)
     self.p_stem = igemm.stem_fprop(self.xp, st.w(self.stem_w), self.stem_raw,
                                    stats=self.stem_bn.stats if tr else None)
     if tr:
-      self.g_stem_act = _buf((B, OH, OW, 64), dev)
+      self.g_stem_act = None if self.fuse_stem else _buf((B, OH, OW, 64), dev)
       self.g_stem_raw = _buf((B, OH, OW, 64), dev)
       self.p_stem_wgrad = igemm.stem_wgrad(self.g_stem_raw, self.xp, st.g(self.stem_w))
 
@@ -293,8 +297,17 @@ class ResNetTrainer(object):
     K.decode_normalize(self.in_u8, self.xp, igemm.STEM_PAD, self.mean, self.std)
     (self.p_stem_remote if remote else self.p_stem).run()
     rv = self.serpentine
-    self.stem_bn.forward(self.stem_raw, self.stem_act, None, 1, training)
-    K.maxpool_fwd(self.stem_act, self.pool, self.pool_idx, 3, 2, 1)
+    if training and self.fuse_stem:
+      # BN + ReLU + max pool in one pass over the raw conv output (csrc/stem_fused.cu): the
+      # 411 MB stem activation is never written
+      bn = self.stem_bn
+      K.stem_bn_relu_pool_fwd(self.stem_raw, self.pool, self.pool_idx, bn.sum, bn.sumsq, bn.gamma,
+                              bn.beta, bn.running_mean, bn.running_var, bn.mean, bn.invstd,
+                              bn.scale, bn.shift, float(self.stem_raw.numel() // bn.C), bn.eps,
+                              bn.momentum)
+    else:
+      self.stem_bn.forward(self.stem_raw, self.stem_act, None, 1, training)
+      K.maxpool_fwd(self.stem_act, self.pool, self.pool_idx, 3, 2, 1)
     for b in self.blocks:
       for u, raw, act in ((b.u1, b.r1, b.a1), (b.u2, b.r2, b.a2)):
         run(u.conv)
@@ -343,9 +356,17 @@ class ResNetTrainer(object):
         b.ds.bn.backward(b.g_out, b.rd, None, b.g_rd, relu=True, mask=b.u3.bn.mask, rev=b.ds.rev)
         b.ds.conv.backward()  # accumulates into g_x
       self.optim.launch(bi)   # buckets that became final start their all-reduce now
-    K.maxpool_bwd(self.g_pool, self.pool_idx, self.g_stem_act, 3, 2, 1)
-    self.stem_bn.backward(self.g_stem_act, self.stem_raw, self.stem_act, self.g_stem_raw,
-                          relu=True, rev=self.stem_rev)
+    if self.fuse_stem:
+      # max-pool backward recomputed inside the BN reduction and the BN apply: the gradient of
+      # the stem activation (411 MB) is never written or read
+      bn = self.stem_bn
+      K.stem_pool_bn_bwd(self.g_pool, self.pool_idx, self.stem_raw, bn.gamma, bn.mean, bn.invstd,
+                         bn.scale, bn.shift, bn.dgamma, bn.dbeta, self.g_stem_raw)
+      ops.count()   # two launches
+    else:
+      K.maxpool_bwd(self.g_pool, self.pool_idx, self.g_stem_act, 3, 2, 1)
+      self.stem_bn.backward(self.g_stem_act, self.stem_raw, self.stem_act, self.g_stem_raw,
+                            relu=True, rev=self.stem_rev)
     self.p_stem_wgrad.run()
 
   # ------------------------------------------------------------------ API

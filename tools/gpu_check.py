@@ -1064,6 +1064,53 @@ def folded_inference():
   return ok
 
 
+@check
+def stem_fused():
+  """Fused stem tail (csrc/stem_fused.cu): BN + ReLU + 3x3/2 max pool forward and the max-pool
+  backward folded into the BN backward, against PyTorch fp32 autograd of the same three layers."""
+  import torch
+  import torch.nn.functional as F
+  from tensorflowonspark_b200 import ops
+  K = ops.K
+  ok = True
+  for (N, H, W, C) in [(4, 112, 112, 64), (3, 37, 41, 64)]:
+    x = (torch.randn(N, H, W, C, device="cuda") * 1.7 + 0.4).bfloat16()
+    gamma, beta = torch.rand(C, device="cuda") + 0.5, 0.3 * torch.randn(C, device="cuda")
+    z = lambda: torch.zeros(C, device="cuda")  # noqa: E731
+    s, ss = z(), z()
+    K.bn_stats(x.view(-1, C), s, ss)
+    rm, rv, mean, invstd, scale, shift = z(), z() + 1, z(), z(), z(), z()
+    OH, OW = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+    y = torch.empty(N, OH, OW, C, device="cuda", dtype=torch.bfloat16)
+    idx = torch.empty(N, OH, OW, C, device="cuda", dtype=torch.uint8)
+    K.stem_bn_relu_pool_fwd(x, y, idx, s, ss, gamma, beta, rm, rv, mean, invstd, scale, shift,
+                            float(N * H * W), 1e-5, 0.1)
+    xf = x.float().requires_grad_(True)
+    g32, b32 = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    m, v = xf.mean((0, 1, 2)), xf.var((0, 1, 2), unbiased=False)
+    act = torch.relu((xf - m) / torch.sqrt(v + 1e-5) * g32 + b32)
+    # the pool sees the activation as the un-fused path would have stored it (bf16): with 8
+    # mantissa bits exact ties inside a window are common and the arg-max - hence where the
+    # gradient lands - must be decided on the same values (straight-through rounding)
+    act = act + (act.bfloat16().float() - act).detach()
+    pooled = F.max_pool2d(act.permute(0, 3, 1, 2), 3, 2, 1)
+    tag = "{}x{}x{}".format(N, H, W)
+    ok &= _report("stem fused {}: mean".format(tag), _rel(mean, m), 1e-3)
+    ok &= _report("stem fused {}: pooled output".format(tag), _rel(y, pooled.permute(0, 2, 3, 1)), 2e-2)
+    ok &= _report("stem fused {}: running var".format(tag),
+                  _rel(rv, 0.9 + 0.1 * xf.detach().var((0, 1, 2), unbiased=True)), 1e-3)
+    gp = torch.randn(N, OH, OW, C, device="cuda").bfloat16()
+    pooled.backward(gp.float().permute(0, 3, 1, 2))
+    dgamma, dbeta = z(), z()
+    dx = torch.empty_like(x)
+    K.stem_pool_bn_bwd(gp, idx, x, gamma, mean, invstd, scale, shift, dgamma, dbeta, dx)
+    torch.cuda.synchronize()
+    ok &= _report("stem fused {}: dgamma".format(tag), _rel(dgamma, g32.grad), 2e-2)
+    ok &= _report("stem fused {}: dbeta".format(tag), _rel(dbeta, b32.grad), 2e-2)
+    ok &= _report("stem fused {}: dx".format(tag), _rel(dx, xf.grad), 3e-2)
+  return ok
+
+
 def main():
   names = sys.argv[1:]
   if names:
