@@ -23,8 +23,8 @@ REPO_DIR = os.path.dirname(PKG_DIR)
 CSRC_DIR = os.path.join(REPO_DIR, "csrc")
 EXT_DIR = os.path.join(PKG_DIR, "_ext")
 
-SOURCES = ["binding.cpp", "igemm.cu", "igemm_wgrad.cu", "elementwise.cu", "bn_bwd.cu", "stem_fused.cu", "smallops.cu", "optim_comm.cu",
-           "feed.cc", "tfrecord.cc", "vmm.cc"]
+SOURCES = ["binding.cpp", "igemm.cu", "igemm_wgrad.cu", "elementwise.cu", "bn_bwd.cu", "stem_fused.cu",
+           "smallops.cu", "optim_comm.cu", "feed.cc", "tfrecord.cc", "vmm.cc"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--expt-relaxed-constexpr", "--use_fast_math"]
 
