@@ -30,6 +30,10 @@ KERNELS = [
     ("ps_apply_momentum", r"ps_apply_kernel<1>"),
     ("ps_push_slot", r"ps_push_slot_kernel"),
     ("ps_pull_model", r"ps_pull_model_kernel"),
+    ("stem_bn_relu_pool_fwd", r"stem_bn_relu_pool_fwd_kernel"),
+    ("stem_pool_bn_bwd_reduce", r"stem_pool_bn_bwd_reduce_kernel"),
+    ("stem_pool_bn_bwd_apply", r"stem_pool_bn_bwd_apply_kernel"),
+    ("igemm_fwd_256_generic_bias_relu_accumulate", r"igemm_fwd_kernel<256, false, 4, 1>"),
     ("bn_fwd_apply_finalize", r"bn_fwd_apply_kernel<true>"),
     ("bn_bwd_apply", r"bn_bwd_apply_kernel"),
     ("bn_bwd_reduce", r"bn_bwd_reduce_kernel"),
