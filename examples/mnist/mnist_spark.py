@@ -18,28 +18,34 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 def main_fun(args, ctx):
   import mnist_common
+  from tensorflowonspark_b200 import TFNode
   from tensorflowonspark_b200.utils import checkpoint
-  step_fn, export_fn, desc = mnist_common.make_trainer(ctx, args.batch_size, args.learning_rate)
-  print("{}:{} using {}".format(ctx.job_name, ctx.task_index, desc))
+  trainer = mnist_common.Trainer(ctx, args.batch_size, args.learning_rate)
+  print("{}:{} using {}".format(ctx.job_name, ctx.task_index, trainer.desc))
+  model_dir = TFNode.local_path(ctx.absolute_path(args.model_dir)) if args.model_dir else None
   feed = ctx.get_data_feed(train_mode=True)
   # every step is a collective: stop at 90 % of the expected steps so that a worker whose
   # partitions were shorter never leaves its peers waiting (same guard as the reference, :62-66)
   steps = int(args.num_examples * args.epochs * 0.9 / (args.batch_size * ctx.num_workers))
   timer = mnist_common.StepTimer()
+  done = 0
   for step in range(steps):
     # columnar fast path: one [B, 785] array sliced out of the shared-memory ring - the rows are
     # never expanded into python lists (the reference pulls them one by one, next_batch(1))
     cols = feed.next_batch_arrays(args.batch_size)
     if not cols or len(cols[0]) < args.batch_size:
       break
-    loss = step_fn(cols[0][:, 1:], cols[0][:, 0])
+    loss = trainer.step(cols[0][:, 1:], cols[0][:, 0])
+    done = step + 1
     timer.tick(step, loss, args.batch_size * ctx.num_workers)
-    if ctx.is_chief and args.model_dir and (step + 1) % args.save_steps == 0:
-      pass  # checkpointing of the torch/native model happens at export below
+    # the chief's weights-NNNN checkpoints (ModelCheckpoint callback of the reference, :57-60);
+    # each one carries the serving signature, so TFModel can score straight from model_dir
+    if ctx.is_chief and model_dir and done % args.save_steps == 0:
+      checkpoint.save(model_dir, done, trainer.state_dict(), model=trainer.served_model())
+  if ctx.is_chief and model_dir and done % args.save_steps:
+    checkpoint.save(model_dir, done, trainer.state_dict(), model=trainer.served_model())
   if args.export_dir:
-    export_fn(args.export_dir, ctx.is_chief)
-  if ctx.is_chief and args.model_dir:
-    checkpoint.save(ctx.absolute_path(args.model_dir), steps, {"steps": steps})
+    trainer.export(args.export_dir, ctx.is_chief)
   feed.terminate()
 
 

@@ -39,6 +39,10 @@ def test_baseline_config_1_mnist_inputmode_spark_sync_sgd_local2(mnist):
               "--model_dir", mnist + "/model_spark"])
   assert "gloo, world 2" in out                       # two CPU workers in one process group
   assert os.path.exists(mnist + "/export_spark/weights.pt")
+  from tensorflowonspark_b200.utils import checkpoint
+  step, state = checkpoint.load(mnist + "/model_spark")   # the chief's periodic weights checkpoint
+  assert step > 0 and len(state) > 1
+  assert os.path.exists(mnist + "/model_spark/signature.json")
   losses = [float(x) for x in re.findall(r"loss ([\d.]+)", out)]
   assert not losses or losses[-1] < 2.4               # (fewer than 100 steps print nothing)
   inf = _run(["examples/mnist/mnist_inference.py", "--cluster_size", "2", "--images_labels",
