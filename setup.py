@@ -9,7 +9,7 @@ from setuptools import find_packages, setup
 
 setup(
     name="tensorflowonspark-b200",
-    version="0.1.0",
+    version="0.2.0",
     description="B200-native (sm_100a) framework with the capabilities of TensorFlowOnSpark",
     packages=find_packages(include=["tensorflowonspark_b200*", "tensorflowonspark*"]),
     package_data={"tensorflowonspark_b200": ["_ext/*.so"]},

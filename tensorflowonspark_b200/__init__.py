@@ -5,4 +5,4 @@ import logging
 logging.basicConfig(level=logging.INFO,
                     format="%(asctime)s %(levelname)s (%(threadName)s-%(process)d) %(message)s")
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"
