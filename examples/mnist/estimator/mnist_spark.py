@@ -30,7 +30,8 @@ def main_fun(args, ctx):
     est.load_state_dict(state)
     print("{}:{} resumed from {} (step {})".format(ctx.job_name, ctx.task_index, latest, step))
   feed = ctx.get_data_feed(train_mode=True)
-  timer = mnist_common.StepTimer()
+  timer = mnist_common.StepTimer(logdir=model_dir if ctx.is_chief else None)
+  loss = None
   # each rank must take the same number of collective steps: stop at 90 % of the expected feed
   max_steps = args.max_steps or int(args.num_examples * args.epochs * 0.9
                                      / ctx.world_size / args.batch_size)
@@ -44,6 +45,7 @@ def main_fun(args, ctx):
     timer.tick(step, loss, args.batch_size * ctx.world_size)
     if ctx.is_chief and step % args.save_checkpoints_steps == 0:
       checkpoint.save(model_dir, step, est.state_dict())
+  timer.close(step, loss)
   if ctx.is_chief:
     checkpoint.save(model_dir, step, est.state_dict())
   if args.export_dir:   # before terminate(): the driver only grants grace_secs after the feed ends

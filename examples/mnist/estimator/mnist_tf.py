@@ -41,6 +41,8 @@ def main_fun(args, ctx):
   if ctx.job_name == "evaluator":
     est = mnist_common.Trainer(ctx, args.batch_size, args.learning_rate, train=False)
     images, labels = _load(sorted(glob.glob(os.path.join(root, "test", "part-*"))))
+    from tensorflowonspark_b200.utils import summary
+    events = summary.SummaryWriter(os.path.join(model_dir, "eval"), flush_secs=0)   # tf.estimator's eval/ dir
     seen = None
     while True:   # stopped by the driver through the control queue at shutdown
       latest = checkpoint.latest_checkpoint(model_dir)
@@ -51,6 +53,7 @@ def main_fun(args, ctx):
         print("evaluator: step {} loss {:.4f} accuracy {:.4f}".format(step, loss, acc))
         with open(os.path.join(model_dir, "eval.log"), "a") as f:
           f.write("{} {:.6f} {:.6f}\n".format(step, loss, acc))
+        events.add_scalars({"loss": loss, "accuracy": acc}, step)
         seen = latest
       time.sleep(args.eval_interval)
 
@@ -61,13 +64,15 @@ def main_fun(args, ctx):
   steps = args.max_steps or int(args.num_examples * args.epochs * 0.9 / ctx.world_size
                                 ) // args.batch_size
   rng = np.random.RandomState(ctx.rank)
-  timer = mnist_common.StepTimer()
+  timer = mnist_common.StepTimer(logdir=model_dir if ctx.is_chief else None)
+  step, loss = 0, None
   for step in range(1, steps + 1):
     idx = rng.randint(0, len(images), args.batch_size)
     loss = est.step(images[idx], labels[idx])
     timer.tick(step, loss, args.batch_size * ctx.world_size)
     if ctx.is_chief and (step % args.save_checkpoints_steps == 0 or step == steps):
       checkpoint.save(model_dir, step, est.state_dict())
+  timer.close(step, loss)
   if args.export_dir:
     est.export(args.export_dir, ctx.is_chief)
 

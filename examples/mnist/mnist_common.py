@@ -110,13 +110,29 @@ def make_trainer(ctx, batch_size, lr):
 
 
 class StepTimer(object):
+  """Console progress every ``every`` steps and, when ``logdir`` is given (the chief's model_dir),
+  the same scalars as TensorBoard events - the role of the Keras ``TensorBoard`` callback in the
+  reference examples (mnist_tf.py:62); ``TFCluster.run(tensorboard=True, log_dir=...)`` serves them."""
 
-  def __init__(self, every=100):
+  def __init__(self, every=100, logdir=None):
     self.every, self.t0, self.n = every, time.time(), 0
+    self.writer = None
+    if logdir:
+      from tensorflowonspark_b200.utils import summary
+      self.writer = summary.SummaryWriter(logdir)
 
   def tick(self, step, loss, batch):
     self.n += 1
     if self.n % self.every == 0:
       dt = time.time() - self.t0
       print("step {:6d} loss {:.4f}  {:.0f} images/s".format(step, loss, self.every * batch / dt))
+      if self.writer is not None:
+        self.writer.add_scalars({"loss": loss, "images_per_s": self.every * batch / dt}, step)
       self.t0 = time.time()
+
+  def close(self, step=None, loss=None):
+    if self.writer is not None:
+      if step is not None and loss is not None:
+        self.writer.add_scalar("loss", loss, step)
+      self.writer.close()
+      self.writer = None

@@ -27,8 +27,8 @@ def main_fun(args, ctx):
   # every step is a collective: stop at 90 % of the expected steps so that a worker whose
   # partitions were shorter never leaves its peers waiting (same guard as the reference, :62-66)
   steps = int(args.num_examples * args.epochs * 0.9 / (args.batch_size * ctx.num_workers))
-  timer = mnist_common.StepTimer()
-  done = 0
+  timer = mnist_common.StepTimer(logdir=model_dir if ctx.is_chief else None)
+  done, loss = 0, None
   for step in range(steps):
     # columnar fast path: one [B, 785] array sliced out of the shared-memory ring - the rows are
     # never expanded into python lists (the reference pulls them one by one, next_batch(1))
@@ -44,6 +44,7 @@ def main_fun(args, ctx):
       checkpoint.save(model_dir, done, trainer.state_dict(), model=trainer.served_model())
   if ctx.is_chief and model_dir and done % args.save_steps:
     checkpoint.save(model_dir, done, trainer.state_dict(), model=trainer.served_model())
+  timer.close(done, loss)
   if args.export_dir:
     trainer.export(args.export_dir, ctx.is_chief)
   feed.terminate()
@@ -84,7 +85,7 @@ if __name__ == "__main__":
 
   cluster = TFCluster.run(sc, main_fun, args, args.cluster_size, num_ps=0,
                           tensorboard=args.tensorboard, input_mode=TFCluster.InputMode.SPARK,
-                          master_node="chief")
+                          log_dir=args.model_dir, master_node="chief")
   cluster.train(images_labels, args.epochs)
   cluster.shutdown(grace_secs=5)
   sc.stop()

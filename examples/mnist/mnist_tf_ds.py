@@ -46,8 +46,8 @@ def main_fun(args, ctx):
   # every rank must take the same number of collective steps: the executor with the fewest records
   # would end first ("Out of Range" in the reference), so the loop is bounded up front
   steps_per_epoch = int(args.num_examples * 0.9) // (args.batch_size * ctx.world_size)
-  timer = mnist_common.StepTimer()
-  step = 0
+  timer = mnist_common.StepTimer(logdir=model_dir if ctx.is_chief else None)
+  step, loss = 0, None
   for images, labels in ds:
     if step >= steps_per_epoch * args.epochs:
       break
@@ -57,6 +57,7 @@ def main_fun(args, ctx):
     if step % steps_per_epoch == 0 and ctx.is_chief:     # ModelCheckpoint(save_weights_only=True)
       path = checkpoint.save(model_dir, step, trainer.state_dict(), model=trainer.served_model())
       print("epoch {}: saved weights to {}".format(step // steps_per_epoch, path))
+  timer.close(step, loss)
   assert step == steps_per_epoch * args.epochs, "input ran dry after {} steps".format(step)
   if args.export_dir:
     trainer.export(args.export_dir, ctx.is_chief)
@@ -84,6 +85,6 @@ if __name__ == "__main__":
                                                                     str(args.cluster_size)))
   cluster = TFCluster.run(sc, main_fun, args, args.cluster_size, num_ps=0,
                           tensorboard=args.tensorboard, input_mode=TFCluster.InputMode.TENSORFLOW,
-                          master_node="chief")
+                          log_dir=args.model_dir, master_node="chief")
   cluster.shutdown(grace_secs=5)
   sc.stop()

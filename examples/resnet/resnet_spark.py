@@ -27,6 +27,7 @@ def parse(argv):
   p.add_argument("--model_dir", default=None)
   p.add_argument("--save_steps", type=int, default=0)
   p.add_argument("--no_graph", action="store_true")
+  p.add_argument("--tensorboard", action="store_true")
   p.add_argument("--metrics", default=None, help="JSONL file for per-step metrics")
   return p.parse_args(argv)
 
@@ -64,6 +65,10 @@ def main_fun(argv, ctx):
   if not args.no_graph:
     net.capture()
   log = metrics.StepLogger(args.metrics, rank=ctx.rank) if args.metrics else None
+  events = None
+  if args.model_dir and ctx.is_chief:     # TensorBoard scalars next to the checkpoints
+    from tensorflowonspark_b200.utils import summary
+    events = summary.SummaryWriter(ctx.absolute_path(args.model_dir))
   torch.cuda.synchronize()
   t0 = time.time()
   for step in range(start, start + args.train_steps):
@@ -79,11 +84,15 @@ def main_fun(argv, ctx):
         print("step {:5d} loss {:.4f}  {:.0f} images/s".format(step + 1, float(loss), rate))
       if log:
         log.log(step=step + 1, loss=float(loss), images_per_s=rate, step_ms=dt * 100)
+      if events:
+        events.add_scalars({"loss": float(loss), "images_per_s": rate}, step + 1)
       t0 = time.time()
     if args.model_dir and args.save_steps and (step + 1) % args.save_steps == 0 and ctx.is_chief:
       checkpoint.save(ctx.absolute_path(args.model_dir), step + 1,
                       {"params": net.state_dict(), "optim": net.optim.state_dict()})
   torch.cuda.synchronize()
+  if events:
+    events.close()
 
 
 if __name__ == "__main__":
@@ -96,6 +105,7 @@ if __name__ == "__main__":
       .set("spark.executor.resource.gpu.amount", "1").set("spark.task.resource.gpu.amount", "1")
   sc = SparkContext(conf=conf)
   cluster = TFCluster.run(sc, main_fun, sys.argv, args.cluster_size, num_ps=0,
-                          input_mode=TFCluster.InputMode.TENSORFLOW, master_node="chief")
+                          input_mode=TFCluster.InputMode.TENSORFLOW, master_node="chief",
+                          tensorboard=args.tensorboard, log_dir=args.model_dir)
   cluster.shutdown()
   sc.stop()

@@ -43,6 +43,10 @@ def test_baseline_config_1_mnist_inputmode_spark_sync_sgd_local2(mnist):
   step, state = checkpoint.load(mnist + "/model_spark")   # the chief's periodic weights checkpoint
   assert step > 0 and len(state) > 1
   assert os.path.exists(mnist + "/model_spark/signature.json")
+  from tensorflowonspark_b200.utils import summary
+  (events,) = summary.event_files(mnist + "/model_spark")   # what tensorboard --logdir would read
+  scalars = [e["scalars"] for e in summary.read_events(events) if e["scalars"]]
+  assert scalars and "loss" in scalars[-1]
   losses = [float(x) for x in re.findall(r"loss ([\d.]+)", out)]
   assert not losses or losses[-1] < 2.4               # (fewer than 100 steps print nothing)
   inf = _run(["examples/mnist/mnist_inference.py", "--cluster_size", "2", "--images_labels",
@@ -74,3 +78,22 @@ def test_estimator_pipeline_train_then_serve_newest_checkpoint(mnist):
                 "--model_dir", mnist + "/model_est", "--export_dir", export, "--output",
                 mnist + "/pred_est"])
     assert float(re.search(r"inference accuracy: ([\d.]+)", out).group(1)) > 0.5
+
+
+def test_estimator_tf_mode_with_evaluator_sidecar_and_event_files(mnist):
+  """reference examples/mnist/estimator/mnist_tf.py: chief + evaluator + worker; the evaluator
+  follows the chief's checkpoints and both leave TensorBoard event files under model_dir."""
+  from tensorflowonspark_b200.utils import summary
+  md = mnist + "/model_est_tf"
+  out = _run(["examples/mnist/estimator/mnist_tf.py", "--cluster_size", "3", "--images_labels",
+              mnist + "/data/tfr", "--num_examples", "2048", "--epochs", "2", "--batch_size", "32",
+              "--learning_rate", "0.05", "--model_dir", md, "--export_dir", mnist + "/export_est_tf",
+              "--save_checkpoints_steps", "10", "--eval_interval", "0.3"])
+  assert "evaluator:0 received the stop signal" in out
+  evals = [line.split() for line in open(md + "/eval.log")]
+  assert evals and float(evals[-1][2]) > 0.3            # accuracy of the last evaluated checkpoint
+  (train_events,) = summary.event_files(md)
+  assert any("loss" in e["scalars"] for e in summary.read_events(train_events))
+  (eval_events,) = summary.event_files(md + "/eval")
+  acc = [e["scalars"]["accuracy"] for e in summary.read_events(eval_events) if e["scalars"]]
+  assert len(acc) == len(evals) and abs(acc[-1] - float(evals[-1][2])) < 1e-5
