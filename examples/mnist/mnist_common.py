@@ -19,7 +19,7 @@ class Trainer(object):
     self.native = bool(ctx.gpus) and torch.cuda.is_available()
     if self.native:
       torch.cuda.set_device(0)
-      comm = ctx.symmetric_comm() if world > 1 else None
+      comm = ctx.gradient_comm() if world > 1 else None
       self.net = mnist.MnistTrainer(batch=batch_size, device="cuda:0", lr=lr, comm=comm)
       if comm is not None:
         comm.broadcast("weights", root=0)

@@ -71,7 +71,7 @@ def main_fun(argv, ctx):
   world = 1 if args.ds in ("off", "one_device") else ctx.world_size
   torch.cuda.set_device(0 if ctx.gpus else int(os.environ.get("LOCAL_RANK", "0")))
   dev = torch.device("cuda", torch.cuda.current_device())
-  comm = ctx.symmetric_comm() if world > 1 else None
+  comm = ctx.gradient_comm() if world > 1 else None
   B = args.batch_size
   from tensorflowonspark_b200.utils import fault
   net = resnet.CifarResNetTrainer(depth=args.resnet_size, batch=B, device=dev, comm=comm,

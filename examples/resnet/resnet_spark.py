@@ -40,7 +40,7 @@ def main_fun(argv, ctx):
   args = parse(argv[1:])
   from tensorflowonspark_b200.utils import fault
   torch.cuda.set_device(0)  # the node runtime made the assigned GPU device 0
-  comm = ctx.symmetric_comm() if ctx.world_size > 1 else None
+  comm = ctx.gradient_comm() if ctx.world_size > 1 else None   # one host: P2P/NVLS kernels; several: NCCL
   B = args.batch_size
   if args.model == "resnet56":
     net = resnet.CifarResNetTrainer(depth=56, batch=B, device="cuda:0", comm=comm,

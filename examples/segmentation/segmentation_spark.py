@@ -37,7 +37,7 @@ def main_fun(args, ctx):
   from tensorflowonspark_b200.models import unet
   from tensorflowonspark_b200.utils import fault
   torch.cuda.set_device(0)
-  comm = ctx.symmetric_comm() if ctx.world_size > 1 else None
+  comm = ctx.gradient_comm() if ctx.world_size > 1 else None   # one host: P2P/NVLS kernels; several: NCCL
   B = args.batch_size
   net = unet.UNetTrainer(batch=B, image=IMG, classes=3, device="cuda:0", lr=args.learning_rate,
                          comm=comm)

@@ -102,6 +102,25 @@ class TFNodeContext(object):
     from .parallel import process_group
     return process_group.symm_from_ctx(self, ranks)
 
+  def worker_hosts(self):
+    """Host of every worker rank, in rank order (master / chief first, then the workers)."""
+    out = []
+    for job in ("master", "chief", "worker"):
+      out.extend(a.rsplit(":", 1)[0] for a in self.cluster_spec.get(job, []))
+    return out
+
+  @property
+  def single_host(self):
+    """True when every worker rank of the job runs on one machine (one NVLink domain)."""
+    return len(set(self.worker_hosts())) <= 1
+
+  def gradient_comm(self):
+    """The communicator a trainer passes as ``comm=``: peer-mapped symmetric memory with the fused
+    P2P / NVLS all-reduce + optimizer kernels when all workers share a host, otherwise the
+    torch.distributed (NCCL / gloo) fallback of parallel/group_comm.py that crosses hosts."""
+    from .parallel import process_group
+    return process_group.gradient_comm_from_ctx(self)
+
   def new_group(self, ranks, backend=None):
     """A torch.distributed sub-group of worker ranks (collective: every rank of the job calls it,
     as torch requires); returns the group, or None on ranks outside it."""

@@ -264,7 +264,11 @@ class UNetTrainer(object):
     torch.cuda.current_stream(self.device).wait_stream(s)
     torch.cuda.synchronize(self.device)
     g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g):
+    # cross-host communicator: its collectives stay outside the graph (FusedOptimizer.finish()
+    # defers them), but the process group's watchdog thread may still poll events of the warm-up
+    # collectives - thread-local capture keeps that from invalidating the capture
+    mode = "thread_local" if getattr(self.optim, "group_mode", False) else "global"
+    with torch.cuda.graph(g, capture_error_mode=mode):
       self.step_kernels()
     self.graph = g
 
@@ -273,6 +277,7 @@ class UNetTrainer(object):
       self.set_input(images_u8, labels)
     if self.graph is not None:
       self.graph.replay()
+      self.optim.after_replay()   # cross-host communicator: all-reduce + update outside the graph
     else:
       self.step_kernels()
     return self.loss_sum

@@ -14,6 +14,12 @@ backward pass as soon as the gradients of that range are final; the kernels then
 run on a dedicated communication stream, overlapped with the rest of backward,
 and ``finish()`` joins the streams (``exposed_ms()`` reports how long that join
 actually waited).  ``step()`` = everything at once on the current stream.
+
+Across hosts (``comm`` is a parallel/group_comm.GroupComm) the peer loads are replaced by a
+``torch.distributed`` all-reduce of each bucket, followed by the same kernel in its single-rank
+form with scale 1 / world, replicated on every rank.  The collective is not recorded into a
+CUDA graph: while a trainer captures its step, ``finish()`` only notes that the update is due,
+and ``after_replay()`` - called by the trainers after every graph replay - runs it eagerly.
 """
 import torch
 
@@ -30,15 +36,19 @@ class FusedOptimizer(object):
     self.opt = OPTS[opt]
     dev = store.master.device
     self.device = dev
-    self.world = comm.world if comm is not None else 1
-    self.rank = comm.rank if comm is not None else 0
-    self.hyper = torch.tensor([lr, momentum, weight_decay, 1.0 / self.world, beta1, beta2, eps, 0.0],
+    # group mode: gradients travel through torch.distributed, the kernel sees a world of one
+    self.group_mode = bool(getattr(comm, "cross_host", False))
+    self.gworld = comm.world if comm is not None else 1
+    self.world = 1 if (comm is None or self.group_mode) else comm.world
+    self.rank = 0 if (comm is None or self.group_mode) else comm.rank
+    self.deferred = False
+    self.hyper = torch.tensor([lr, momentum, weight_decay, 1.0 / self.gworld, beta1, beta2, eps, 0.0],
                               dtype=torch.float32, device=dev)
     # with peers, the optimizer state lives in symmetric memory like the master copy: a rank only
     # ever updates its own shard of each bucket, so whoever saves a checkpoint pulls the other
     # shards over NVLink (assemble())
     def _state(name):
-      if comm is not None and self.world > 1:
+      if comm is not None and self.world > 1:    # (never in group mode: the state is replicated)
         t = comm.alloc(name, store.total, torch.float32)
         t.zero_()
         return t
@@ -68,7 +78,7 @@ class FusedOptimizer(object):
           "grid": self.grid, "zero_grads": 0,
           "aux_begin": store.decay_end,
       }
-      if comm is None:
+      if comm is None or self.group_mode:
         d["grads"] = [store.grads.data_ptr()]
         d["weights"] = [store.weights.data_ptr()]
         d["aux32"] = [store.aux32.data_ptr()]
@@ -133,7 +143,7 @@ class FusedOptimizer(object):
   def launch(self, tag):
     """Gradients of every bucket tagged ``tag`` are final on the current stream: run their
     fused all-reduce + update on the communication stream now."""
-    if not self.overlap:
+    if not self.overlap or self._capturing_group():
       return
     if not self._launched:
       self._bump_step()
@@ -145,13 +155,17 @@ class FusedOptimizer(object):
       self.comm_stream.wait_event(self._ev_ready[i])
       self._join_producers(self.comm_stream, i)
       with torch.cuda.stream(self.comm_stream):
-        ops.K.allreduce_opt(self._args[i])
+        self._run_bucket(i)
       self._launched.add(i)
 
   def finish(self):
     """Launch whatever has not been launched and make the current stream wait for all of it."""
+    if self._capturing_group():
+      self.deferred = True      # the collective stays outside the graph: after_replay() runs it
+      return
     if not self.overlap:
-      self._join_producers(torch.cuda.current_stream(self.device), "finish")
+      if self.device.type == "cuda":
+        self._join_producers(torch.cuda.current_stream(self.device), "finish")
       return self.step()
     for tag in list(self._by_tag):
       self.launch(tag)
@@ -176,10 +190,35 @@ class FusedOptimizer(object):
   def step(self, bucket=None):
     """Launch the fused kernel for one bucket (or all) on the current stream.  Stream order
     guarantees this rank's gradients are complete; the kernel's flag barrier covers the peers."""
+    if self._capturing_group():
+      self.deferred = True      # see finish()
+      return
     self._bump_step()
     todo = range(len(self.buckets)) if bucket is None else [bucket]
     for i in todo:
-      ops.K.allreduce_opt(self._args[i])
+      self._run_bucket(i)
+
+  def _run_bucket(self, i):
+    if self.group_mode:
+      b, e, _ = self.buckets[i]
+      self.comm.all_reduce(self.store.grads[b:e])     # SUM; the kernel scales by 1 / world
+    ops.K.allreduce_opt(self._args[i])
+
+  def _capturing_group(self):
+    return (self.group_mode and self.device.type == "cuda"
+            and torch.cuda.is_current_stream_capturing())
+
+  def after_replay(self):
+    """Trainers call this after ``graph.replay()``: in group mode the captured step ends with the
+    local gradients complete and this runs all-reduce + update eagerly; otherwise a no-op."""
+    if self.deferred:
+      self._launched = set()
+      if self.overlap:
+        for tag in list(self._by_tag):
+          self.launch(tag)
+        torch.cuda.current_stream(self.device).wait_stream(self.comm_stream)
+      else:
+        self.step()
 
   # ------------------------------------------------------ sharded state
   def shard_bounds(self, bucket, rank):

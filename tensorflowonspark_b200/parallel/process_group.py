@@ -60,6 +60,14 @@ def symm_from_ctx(ctx, ranks=None):
   position in / size of that group, and its exchanges use a board namespace of their own."""
   from .. import reservation
   from . import symm
+  hosts = ctx.worker_hosts() if hasattr(ctx, "worker_hosts") else []
+  span = sorted(set(hosts[r] for r in (ranks if ranks is not None else range(len(hosts)))
+                    if 0 <= int(r) < len(hosts)))
+  if len(span) > 1:
+    raise RuntimeError(
+        "symmetric memory maps peer GPUs through CUDA IPC and needs every member on one host, but "
+        "the group spans {}; use ctx.gradient_comm() (NCCL between hosts) or pass ranks= of one "
+        "host".format(span))
   if ranks is None:
     members = list(range(ctx.world_size))
   else:
@@ -83,3 +91,16 @@ def symm_from_ctx(ctx, ranks=None):
     return client.all_gather(tag, me, size, obj)
 
   return symm.SymmComm(me, size, exchange, ctx.device)
+
+
+def gradient_comm_from_ctx(ctx):
+  """SymmComm on one host, GroupComm (torch.distributed) across hosts or without a GPU;
+  ``TFOS_GRADIENT_COMM=group`` forces the latter (e.g. GPUs of one host without P2P access)."""
+  import torch
+  force = os.environ.get("TFOS_GRADIENT_COMM", "auto")
+  use_cuda = bool(ctx.gpus) and torch.cuda.is_available()
+  if force != "group" and use_cuda and ctx.single_host:
+    return symm_from_ctx(ctx)
+  from . import group_comm
+  init_from_ctx(ctx)
+  return group_comm.GroupComm(device=ctx.device)

@@ -191,3 +191,32 @@ def test_subgroups_process_group_and_board_namespaces(sc, monkeypatch):
     assert rec["pair"]["rank"] == r and rec["pair"]["world"] == 2
     assert [x["r"] for x in rec["pair"]["gathered"]] == [0, 1]
     assert rec["alone"] == {"rank": 0, "world": 1, "gathered": [{"r": r}]}
+
+
+def test_gradient_comm_falls_back_to_the_process_group_without_gpus(sc):
+  """ctx.gradient_comm(): no GPU (or several hosts) -> GroupComm over torch.distributed; its
+  alloc / broadcast / all_reduce are what a trainer and FusedOptimizer's group mode call."""
+  import tempfile
+  d = tempfile.mkdtemp()
+
+  def fn(args, ctx):
+    import json
+    import torch
+    comm = ctx.gradient_comm()
+    w = comm.alloc("weights", 16, torch.float32)
+    w.fill_(float(ctx.rank + 5))
+    comm.broadcast("weights", root=0)          # the chief's initial values win
+    g = torch.full((16,), float(ctx.rank + 1))
+    comm.all_reduce(g)
+    comm.barrier()
+    with open("{}/{}".format(args["d"], ctx.rank), "w") as f:
+      json.dump({"kind": type(comm).__name__, "world": comm.world, "rank": comm.rank,
+                 "single_host": ctx.single_host, "w": float(w[3]), "g": float(g[7])}, f)
+
+  cluster = TFCluster.run(sc, fn, {"d": d}, 2, 0, input_mode=TFCluster.InputMode.TENSORFLOW,
+                          master_node="chief")
+  cluster.shutdown()
+  import json
+  res = [json.load(open("{}/{}".format(d, r))) for r in range(2)]
+  for r, rec in enumerate(res):
+    assert rec == {"kind": "GroupComm", "world": 2, "rank": r, "single_host": True, "w": 5.0, "g": 3.0}

@@ -1111,6 +1111,73 @@ def stem_fused():
   return ok
 
 
+@check
+def group_mode_cross_host():
+  """Cross-host gradient path (parallel/group_comm.py): torch.distributed (NCCL) all-reduce of each
+  bucket + the fused optimizer kernel in its single-rank form, the update deferred around the
+  captured step (FusedOptimizer.after_replay).  A one-rank NCCL group makes the all-reduce the
+  identity, so the weights must follow the plain local trainer - through optimizer.step() on the
+  basic-block net and through the bucketed / overlapped launch() + finish() on ResNet-50."""
+  import socket
+  import torch
+  import torch.distributed as dist
+  from tensorflowonspark_b200.models import resnet
+  from tensorflowonspark_b200.parallel import group_comm
+  from tensorflowonspark_b200.parallel.fused_optim import FusedOptimizer
+  created = False
+  if not dist.is_initialized():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    dist.init_process_group("nccl", init_method="tcp://127.0.0.1:{}".format(port), rank=0,
+                            world_size=1, device_id=torch.device("cuda", 0))
+    created = True
+
+  def drive(net, steps=3):
+    x, y = net.synthetic_batch()
+    net.set_input(x, y)
+    w0 = net.store.master.clone()
+    net.train_step()            # eager: launch() / finish() (or step()) run the collective inline
+    net.capture()               # warm-up steps run it eagerly, the capture defers it
+    for _ in range(steps):
+      net.train_step()          # replay + after_replay()
+    torch.cuda.synchronize()
+    return w0, net.store.master.clone(), float(net.loss_sum)
+
+  ok = True
+  try:
+    ref = resnet.CifarResNetTrainer(depth=20, batch=32, lr=0.1)
+    net = resnet.CifarResNetTrainer(depth=20, batch=32, lr=0.1,
+                                    comm=group_comm.GroupComm(device="cuda:0"))
+    assert net.optim.group_mode and not net.optim.overlap
+    w0, wr, lr_ = drive(ref)
+    _, wg, lg = drive(net)
+    moved = float((wr - w0).abs().max())
+    ok &= net.optim.deferred and moved > 1e-3
+    ok &= _report("group mode step(): master vs local trainer (moved {:.3g})".format(moved),
+                  float((wg - wr).abs().max()) / moved, 1e-1)
+
+    comm = group_comm.GroupComm(device="cuda:0")
+    ref = resnet.ResNetTrainer(depth=50, batch=8, image=64, lr=0.05)
+    net = resnet.ResNetTrainer(depth=50, batch=8, image=64, lr=0.05, comm=comm)
+    net.optim = FusedOptimizer(net.store, comm=comm, opt="momentum", lr=0.05, momentum=0.9,
+                               weight_decay=1e-4, buckets=net._comm_buckets())
+    assert net.optim.group_mode and net.optim.overlap and len(net.optim.buckets) == 6
+    w0, wr, lr_ = drive(ref)
+    _, wg, lg = drive(net)
+    moved = float((wr - w0).abs().max())
+    ok &= net.optim.deferred and moved > 1e-3
+    ok &= _report("group mode bucketed launch()/finish(): master vs local (moved {:.3g}, loss {:.3f} "
+                  "vs {:.3f})".format(moved, lg, lr_), float((wg - wr).abs().max()) / moved, 1e-1)
+    sd = net.optim.state_dict()             # replicated state: nothing to assemble
+    ok &= _report("group mode momentum state vs local", _rel(sd["state1"].cuda(), ref.optim.state1), 1e-1)
+  finally:
+    if created:
+      dist.destroy_process_group()
+  return ok
+
+
 def main():
   names = sys.argv[1:]
   if names:
