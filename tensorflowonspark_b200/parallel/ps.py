@@ -289,6 +289,18 @@ class PSServer(object):
 class PSClient(object):
   """Worker-side handle on all parameter servers of the cluster."""
 
+  def __new__(cls, ctx, timeout=600, local_servers=None):
+    # servers that published a TCP endpoint (ps and workers on different hosts, parallel/ps_net.py)
+    # are reached through the network client, which has the same surface
+    if cls is PSClient and not local_servers:
+      board = _board(ctx)
+      first = board.get("ps/{}/0".format(ctx.cluster_id), timeout)
+      board.close()
+      if first.get("kind") == "tcp":
+        from . import ps_net
+        return ps_net.NetPSClient(ctx, timeout)
+    return super(PSClient, cls).__new__(cls)
+
   def __init__(self, ctx, timeout=600, local_servers=None):
     """``local_servers``: PSServer objects living in THIS process (single-process use and the
     kernel checks) - their memory is addressed directly instead of through CUDA IPC, which
@@ -530,9 +542,12 @@ class PSWorker(object):
     return net.loss_sum
 
 
-def attach(ctx, params=None, init=None, **server_kwargs):
+def attach(ctx, params=None, init=None, transport=None, **server_kwargs):
   """PSServer on a 'ps' node (``params`` = number of elements or an initial flat tensor;
-  ``optimizer=...`` and its hyper-parameters select slot mode), PSClient everywhere else."""
+  ``optimizer=...`` and its hyper-parameters select slot mode), PSClient everywhere else.
+  ``transport``: 'ipc' | 'tcp' for the servers (default: by the hosts of the cluster spec, see
+  :func:`transport`); clients follow what the servers published."""
+  choose = globals()["transport"]
   if ctx.job_name == "ps":
     if params is None:
       raise ValueError("a ps node must be told the parameter count: start_cluster_server(params=N)")
@@ -541,5 +556,19 @@ def attach(ctx, params=None, init=None, **server_kwargs):
       numel = int(params.numel() if hasattr(params, "numel") else params.size)
     else:
       numel = int(params)
+    if (transport or choose(ctx)) == "tcp":
+      from . import ps_net
+      return ps_net.NetPSServer(ctx, numel, init, **server_kwargs)
     return PSServer(ctx, numel, init, **server_kwargs)
   return PSClient(ctx)
+
+
+def transport(ctx):
+  """'ipc' (CUDA IPC / shared memory: every node on one host) or 'tcp' (parallel/ps_net.py);
+  ``TFOS_PS_TRANSPORT`` overrides the choice made from the hosts named in the cluster spec."""
+  import os
+  forced = os.environ.get("TFOS_PS_TRANSPORT", "auto")
+  if forced in ("tcp", "ipc"):
+    return forced
+  hosts = set(a.rsplit(":", 1)[0] for nodes in ctx.cluster_spec.values() for a in nodes)
+  return "tcp" if len(hosts) > 1 else "ipc"

@@ -1178,6 +1178,75 @@ def group_mode_cross_host():
   return ok
 
 
+@check
+def ps_net_gpu():
+  """Parameter server over TCP (parallel/ps_net.py, ps and workers on different hosts) with a GPU
+  ps and a GPU worker: the received gradient is staged through pinned memory into the same
+  ps_apply kernel as the peer-mapped server; pull_model ships bf16 weights + the fp32 tail.
+  Against the optimizer in float64, two servers (slices), two workers."""
+  import torch
+  from tensorflowonspark_b200 import reservation
+  from tensorflowonspark_b200.parallel import ps, ps_net
+  ok = True
+  srv = reservation.Server(1)
+  addr = srv.start()
+
+  class Ctx(object):
+    def __init__(self, job, idx, cid):
+      self.job_name, self.task_index = job, idx
+      self.cluster_spec = {"ps": ["10.0.0.1:1", "10.0.0.2:1"], "chief": ["10.0.0.3:3"], "worker": ["10.0.0.4:4"]}
+      self.cluster_id, self.server_addr, self.gpus = cid, addr, [0]
+
+  total, decay_end, R = 1 << 16, 3 << 14, 1 << 9
+  numel = total + R
+  for opt in ("momentum", "adam"):
+    torch.manual_seed(11)
+    init = torch.randn(numel, device="cuda")
+    servers = [ps.attach(Ctx("ps", i, "net-" + opt), params=init, optimizer=opt, lr=0.05, momentum=0.9,
+                         weight_decay=1e-2, decay_end=decay_end, ema_begin=total, grad_scale=0.5)
+               for i in range(2)]
+    assert all(isinstance(s_, ps_net.NetPSServer) and s_.cuda for s_ in servers)
+    clients = [ps.attach(Ctx("chief", 0, "net-" + opt)), ps.attach(Ctx("worker", 0, "net-" + opt))]
+    weights = torch.zeros(total, device="cuda", dtype=torch.bfloat16)
+    aux = torch.zeros(total - decay_end, device="cuda")
+    w = init.double().clone()
+    m, v, t = torch.zeros_like(w), torch.zeros_like(w), 0
+    for step in range(3):
+      for c in clients:
+        running = torch.zeros(R, device="cuda")
+        c.pull_model(weights, aux, running, decay_end=decay_end, total=total)
+        torch.cuda.synchronize()
+        ok &= _report("ps tcp[{}] pull: bf16 weights".format(opt), _rel(weights, w[:total]), 1e-2)
+        ok &= _report("ps tcp[{}] pull: fp32 tail".format(opt),
+                      _rel(aux, w[decay_end:total]) + _rel(running, w[total:]), 1e-5)
+        grads = torch.randn(total, device="cuda")
+        running += 0.1 * torch.randn(R, device="cuda")
+        c.push_grads(grads, running, total=total)
+        gg = grads.double() * 0.5
+        gg[:decay_end] += 1e-2 * w[:decay_end]
+        if opt == "momentum":
+          m[:total] = 0.9 * m[:total] + gg
+          gg = m[:total]
+        else:
+          t += 1
+          m[:total] = 0.9 * m[:total] + 0.1 * gg
+          v[:total] = 0.999 * v[:total] + 0.001 * gg * gg
+          gg = (m[:total] / (1 - 0.9 ** t)) / (torch.sqrt(v[:total] / (1 - 0.999 ** t)) + 1e-7)
+        w[:total] -= 0.05 * gg
+        w[total:] = running.double()
+    applied = clients[0].applies() + clients[1].applies()      # drains the outstanding pushes
+    got = torch.from_numpy(clients[0].pull()).cuda()
+    ok &= _report("ps tcp[{}] master after 6 applies / slice".format(opt), _rel(got, w),
+                  2e-3 if opt == "adam" else 1e-5)
+    ok &= _report("ps tcp[{}] apply count".format(opt), float(sum(abs(a - 6) for a in applied)), 0.5)
+    for c in clients:
+      c.close()
+    for s_ in servers:
+      s_.close()
+  srv.stop()
+  return ok
+
+
 def main():
   names = sys.argv[1:]
   if names:
