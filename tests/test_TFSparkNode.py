@@ -156,3 +156,40 @@ def test_gpu_index_is_per_host_position_in_the_cluster_spec():
     for job, idx, want in (("chief", 0, 0), ("worker", 0, 1), ("worker", 1, 2), ("worker", 2, 0)):
       TFSparkNode._get_gpus({"num_gpus": 1}, 7, cluster_spec=spec, job_name=job, task_index=idx)
       assert calls[-1] == (1, want, gpu_info.AS_LIST), (job, idx, calls[-1])
+
+
+def test_spark_resource_api_without_gpu_resources_falls_back_to_gpu_info():
+  """reference test_gpu_spark_fallback (:133-152): Spark 3 is there but the job was submitted
+  without spark.executor.resource.gpu.* - the node still finds free GPUs through nvidia-smi."""
+  got = {}
+
+  def fn(args, ctx):
+    got["gpus"], got["visible"] = ctx.gpus, os.environ["CUDA_VISIBLE_DEVICES"]
+
+  tctx = mock.Mock()
+  tctx.resources.return_value = {}
+  with mock.patch.object(TFSparkNode, "_has_spark_resource_api", return_value=True), \
+       mock.patch.object(TFSparkNode.TaskContext, "get", return_value=tctx), \
+       mock.patch.object(gpu_info, "is_gpu_available", return_value=True), \
+       mock.patch.object(gpu_info, "get_gpus", return_value=["5"]) as gg:
+    _run_node(fn, {"num_gpus": 1})
+  assert got["gpus"] == ["5"] and gg.called and got["visible"].split(",")[0] == "5"
+
+
+def test_no_gpu_anywhere_defaults_to_cpu_but_an_explicit_request_fails():
+  """reference test_gpu_spark_unavailable_default / _but_requested (:154-190)."""
+  got = {}
+
+  def fn(args, ctx):
+    got["gpus"], got["visible"] = ctx.gpus, os.environ["CUDA_VISIBLE_DEVICES"]
+
+  tctx = mock.Mock()
+  tctx.resources.return_value = {}
+  with mock.patch.object(TFSparkNode, "_has_spark_resource_api", return_value=True), \
+       mock.patch.object(TFSparkNode.TaskContext, "get", return_value=tctx), \
+       mock.patch.object(gpu_info, "is_gpu_available", return_value=False), \
+       mock.patch.object(gpu_info, "get_gpus") as gg:
+    _run_node(fn, {})
+    assert got == {"gpus": [], "visible": ""} and not gg.called
+    with pytest.raises(Exception, match="requested but none"):
+      _run_node(fn, {"num_gpus": 1})
