@@ -62,6 +62,8 @@ def _stale():
   so = so_path()
   if not os.path.exists(so):
     return True
+  if not os.path.isdir(CSRC_DIR):   # installed without the sources: the shipped .so is the product
+    return False
   t = os.path.getmtime(so)
   for s in os.listdir(CSRC_DIR):
     if os.path.getmtime(os.path.join(CSRC_DIR, s)) > t:
