@@ -7,7 +7,6 @@ side (DFUtil.scala:21-259: schema *hints*; SimpleTypeParser.scala:27-64: the
 ``tf.train.Example`` protos are encoded by the native codec in csrc/tfrecord.cc.
 """
 import logging
-import os
 import re
 
 from . import tfrecord

@@ -818,7 +818,6 @@ def ps_kernels():
   and slot mode (push_slot -> ps_apply with SGD / momentum / Adam + weight decay + the
   non-trainable tail -> pull_model).  Server and client share this process and GPU: the kernels
   are the same ones that run across NVLink, only the pointers are local."""
-  import numpy as np
   import torch
   from tensorflowonspark_b200 import reservation
   from tensorflowonspark_b200.parallel import ps
