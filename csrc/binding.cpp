@@ -498,7 +498,7 @@ void allreduce_opt(const py::dict& d) {
   a.aux32_mc = reinterpret_cast<float*>(geti<uint64_t>(d, "aux32_mc", 0));
   const int opt = geti<int>(d, "opt", 0);
   const int grid = geti<int>(d, "grid", 32);
-  check(tfos::allreduce_opt(a, opt, grid, cur_stream()), "allreduce_opt");
+  check(tfos::allreduce_opt(a, opt, grid, cur_stream(), geti<int>(d, "phase", 0)), "allreduce_opt");
 }
 
 tfos::BcastArgs parse_bcast(const py::dict& d) {

@@ -96,7 +96,8 @@ struct AllreduceOptArgs {
   uint32_t* epoch;          // local, one word per slot
   uint32_t* block_counter;  // local, one word per slot
 };
-cudaError_t allreduce_opt(const AllreduceOptArgs& a, int opt, int grid, cudaStream_t s);
+// phase: 0 = fused; 1 = intra-host reduce-scatter only; 2 = update + all-gather only (optim_comm.cu)
+cudaError_t allreduce_opt(const AllreduceOptArgs& a, int opt, int grid, cudaStream_t s, int phase = 0);
 
 struct BcastArgs {
   int world, rank, root, slot;

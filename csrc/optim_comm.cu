@@ -93,7 +93,12 @@ __device__ __forceinline__ float opt_update(float w, float g, float& s1, float& 
   return w - h[0] * g;
 }
 
-template <int OPT, bool MULTIMEM>
+// PHASE splits the kernel for the hierarchical (several hosts) all-reduce: 1 = intra-host
+// reduce-scatter only (the sum over the local peers of this rank's shard replaces that shard of
+// the rank's OWN gradient buffer - peers only ever read the other shards of it); 2 = update +
+// all-gather only (the gradient comes from the own buffer, which by then holds the sum over all
+// hosts; new weights go to every local peer).  0 = both in one pass (one host).
+template <int OPT, bool MULTIMEM, int PHASE = 0>
 __global__ void __launch_bounds__(512, 1) allreduce_opt_kernel(const AllreduceOptArgs a) {
   __shared__ float h[8];
   if (threadIdx.x < 8) h[threadIdx.x] = a.hyper[threadIdx.x];
@@ -136,9 +141,10 @@ __global__ void __launch_bounds__(512, 1) allreduce_opt_kernel(const AllreduceOp
     const long long i = i0 + u * stride;
     if (i >= hi) break;
     float g[8];
-    if (world == 1) {
-      const float4 g0 = *reinterpret_cast<const float4*>(a.grads[0] + i);
-      const float4 g1 = *reinterpret_cast<const float4*>(a.grads[0] + i + 4);
+    if (world == 1 || PHASE == 2) {
+      const float* own = (PHASE == 2) ? a.grads[rank] : a.grads[0];
+      const float4 g0 = *reinterpret_cast<const float4*>(own + i);
+      const float4 g1 = *reinterpret_cast<const float4*>(own + i + 4);
       g[0] = g0.x, g[1] = g0.y, g[2] = g0.z, g[3] = g0.w;
       g[4] = g1.x, g[5] = g1.y, g[6] = g1.z, g[7] = g1.w;
     } else if (MULTIMEM) {
@@ -165,6 +171,11 @@ __global__ void __launch_bounds__(512, 1) allreduce_opt_kernel(const AllreduceOp
           g[4] += __uint_as_float(v1[p].x), g[5] += __uint_as_float(v1[p].y);
           g[6] += __uint_as_float(v1[p].z), g[7] += __uint_as_float(v1[p].w);
         }
+    }
+    if (PHASE == 1) {
+      *reinterpret_cast<float4*>(a.grads[rank] + i) = make_float4(g[0], g[1], g[2], g[3]);
+      *reinterpret_cast<float4*>(a.grads[rank] + i + 4) = make_float4(g[4], g[5], g[6], g[7]);
+      continue;
     }
     float w[8], s1[8], s2[8];
     const long long li = i - a.state_offset;  // master/state are indexed shard-locally
@@ -540,8 +551,12 @@ __global__ void __launch_bounds__(512) ps_pull_model_kernel(const PsPullArgs a) 
 }
 
 template <int OPT>
-cudaError_t launch_ar(const AllreduceOptArgs& a, int grid, cudaStream_t s) {
-  if (a.grads_mc != nullptr && a.weights_mc != nullptr && a.world > 1)
+cudaError_t launch_ar(const AllreduceOptArgs& a, int grid, cudaStream_t s, int phase) {
+  if (phase == 1)   // (the reduce-scatter half does not depend on the optimizer)
+    allreduce_opt_kernel<kOptSgd, false, 1><<<grid, 512, 0, s>>>(a);
+  else if (phase == 2)
+    allreduce_opt_kernel<OPT, false, 2><<<grid, 512, 0, s>>>(a);
+  else if (a.grads_mc != nullptr && a.weights_mc != nullptr && a.world > 1)
     allreduce_opt_kernel<OPT, true><<<grid, 512, 0, s>>>(a);
   else
     allreduce_opt_kernel<OPT, false><<<grid, 512, 0, s>>>(a);
@@ -550,13 +565,13 @@ cudaError_t launch_ar(const AllreduceOptArgs& a, int grid, cudaStream_t s) {
 
 }  // namespace
 
-cudaError_t allreduce_opt(const AllreduceOptArgs& a, int opt, int grid, cudaStream_t s) {
+cudaError_t allreduce_opt(const AllreduceOptArgs& a, int opt, int grid, cudaStream_t s, int phase) {
   if (a.world < 1 || a.world > kMaxRanks) return cudaErrorInvalidValue;
-  if ((a.begin & 7) != 0) return cudaErrorInvalidValue;
+  if ((a.begin & 7) != 0 || phase < 0 || phase > 2) return cudaErrorInvalidValue;
   switch (opt) {
-    case kOptSgd: return launch_ar<kOptSgd>(a, grid, s);
-    case kOptMomentum: return launch_ar<kOptMomentum>(a, grid, s);
-    case kOptAdam: return launch_ar<kOptAdam>(a, grid, s);
+    case kOptSgd: return launch_ar<kOptSgd>(a, grid, s, phase);
+    case kOptMomentum: return launch_ar<kOptMomentum>(a, grid, s, phase);
+    case kOptAdam: return launch_ar<kOptAdam>(a, grid, s, phase);
     default: return cudaErrorInvalidValue;
   }
 }

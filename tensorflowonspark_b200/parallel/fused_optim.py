@@ -37,10 +37,17 @@ class FusedOptimizer(object):
     dev = store.master.device
     self.device = dev
     # group mode: gradients travel through torch.distributed, the kernel sees a world of one
+    # hierarchical mode (group_comm.HierComm): the kernel's world is the host; the shards are
+    # summed across hosts through torch.distributed between its two halves (PHASE 1 / PHASE 2)
     self.group_mode = bool(getattr(comm, "cross_host", False))
+    self.hier_mode = bool(getattr(comm, "hierarchical", False))
     self.gworld = comm.world if comm is not None else 1
-    self.world = 1 if (comm is None or self.group_mode) else comm.world
-    self.rank = 0 if (comm is None or self.group_mode) else comm.rank
+    if comm is None or self.group_mode:
+      self.world, self.rank = 1, 0
+    elif self.hier_mode:
+      self.world, self.rank = comm.local_world, comm.local_rank
+    else:
+      self.world, self.rank = comm.world, comm.rank
     self.deferred = False
     self.hyper = torch.tensor([lr, momentum, weight_decay, 1.0 / self.gworld, beta1, beta2, eps, 0.0],
                               dtype=torch.float32, device=dev)
@@ -78,7 +85,7 @@ class FusedOptimizer(object):
           "grid": self.grid, "zero_grads": 0,
           "aux_begin": store.decay_end,
       }
-      if comm is None or self.group_mode:
+      if comm is None or self.group_mode or (self.hier_mode and self.world == 1):
         d["grads"] = [store.grads.data_ptr()]
         d["weights"] = [store.weights.data_ptr()]
         d["aux32"] = [store.aux32.data_ptr()]
@@ -199,13 +206,22 @@ class FusedOptimizer(object):
       self._run_bucket(i)
 
   def _run_bucket(self, i):
+    if self.hier_mode:
+      d = self._args[i]
+      if self.world > 1:
+        ops.K.allreduce_opt(dict(d, phase=1))          # NVLink reduce-scatter inside the host
+      lo, hi = self.shard_bounds(i, self.rank)
+      if hi > lo:
+        self.comm.all_reduce_inter(self.store.grads[lo:hi])   # this rank's shard, across hosts
+      ops.K.allreduce_opt(dict(d, phase=2))            # update + all-gather inside the host
+      return
     if self.group_mode:
       b, e, _ = self.buckets[i]
       self.comm.all_reduce(self.store.grads[b:e])     # SUM; the kernel scales by 1 / world
     ops.K.allreduce_opt(self._args[i])
 
   def _capturing_group(self):
-    return (self.group_mode and self.device.type == "cuda"
+    return ((self.group_mode or self.hier_mode) and self.device.type == "cuda"
             and torch.cuda.is_current_stream_capturing())
 
   def after_replay(self):

@@ -82,3 +82,98 @@ class GroupComm(object):
                        "host (GroupComm); use ctx.symmetric_comm() on a single-host group")
 
   flag_ptrs = mc_ptr = peer_ptrs
+
+
+class HierComm(object):
+  """Two-level gradient communicator for several multi-GPU hosts.
+
+  ``local``: the SymmComm of the GPUs of THIS host (None on a one-GPU host), ``inter``: the
+  torch.distributed group of the ranks that have this rank's local index on every host.  The
+  all-reduce of a bucket then is (FusedOptimizer, hierarchical mode):
+
+    1. intra-host reduce-scatter - allreduce_opt kernel, PHASE 1: every rank sums its 1 / L shard
+       of the bucket over the L local peers through peer loads (NVLink) into its own buffer;
+    2. inter-host all-reduce of that shard only (NCCL over the network: 1 / L of the bytes per
+       rank, all L ranks of a host driving their own NICs concurrently);
+    3. update + intra-host all-gather - PHASE 2: optimizer on the shard (scale 1 / global world,
+       state sharded like on one host), new bf16 weights stored to every local peer.
+
+  Network bytes per rank and step are 1 / L of what a flat all-reduce of the whole vector moves
+  through each process, and the optimizer state stays sharded (ZeRO-1-like) inside the host."""
+
+  hierarchical = True
+
+  def __init__(self, local, inter, rank, world, device=None, local_rank=0, local_world=1):
+    import torch.distributed as dist
+    self.local, self.inter = local, inter
+    self.rank, self.world = int(rank), int(world)
+    self.local_rank = local.rank if local is not None else int(local_rank)
+    self.local_world = local.world if local is not None else int(local_world)
+    self.hosts = self.world // max(1, self.local_world)
+    self.device = torch.device(device) if device is not None else (
+        local.device if local is not None else torch.device("cpu"))
+    self.nvls = False
+    self.bufs = {}
+    self._dist = dist
+    logger.info("gradient communicator: %d host(s) x %d GPU(s), rank %d (local %d): NVLink "
+                "reduce-scatter / all-gather inside the host, %s all-reduce of the shards between",
+                self.hosts, self.local_world, self.rank, self.local_rank,
+                dist.get_backend(inter) if inter is not None else "no")
+
+  # ---- buffers: symmetric inside the host --------------------------------------------------
+  def alloc(self, name, numel, dtype, multicast=False):
+    if self.local is not None:
+      t = self.local.alloc(name, numel, dtype, multicast=False)
+    else:
+      t = torch.zeros(int(numel), dtype=dtype, device=self.device)
+    self.bufs[name] = t
+    return t
+
+  def peer_ptrs(self, name):
+    return self.local.peer_ptrs(name) if self.local is not None else [self.bufs[name].data_ptr()]
+
+  def flag_ptrs(self):
+    return self.local.flag_ptrs()
+
+  def epoch_ptr(self, slot):
+    return self.local.epoch_ptr(slot)
+
+  def counter_ptr(self, slot):
+    return self.local.counter_ptr(slot)
+
+  def mc_ptr(self, name):
+    return 0
+
+  # ---- collectives -------------------------------------------------------------------------
+  def all_reduce_inter(self, tensor):
+    """SUM of ``tensor`` over the hosts (the ranks sharing this local index), in place."""
+    if self.inter is not None and self.hosts > 1:
+      self._dist.all_reduce(tensor, op=self._dist.ReduceOp.SUM, group=self.inter)
+
+  def broadcast(self, name, root=0):
+    """Global rank ``root``'s copy of ``name`` wins everywhere: across the hosts among the ranks
+    with the root's local index, then inside every host from that local index."""
+    if root != 0:
+      raise ValueError("HierComm.broadcast: the root is the chief (global rank 0)")
+    if self.local_rank == 0 and self.inter is not None and self.hosts > 1:
+      src = self._dist.get_global_rank(self.inter, 0)
+      self._dist.broadcast(self.bufs[name], src=src, group=self.inter)
+      if self.device.type == "cuda":
+        torch.cuda.current_stream(self.device).synchronize()
+    if self.local is not None:
+      self.local.barrier()              # the local root's copy is complete before anyone pulls it
+      self.local.broadcast(name, root=0)
+
+  def barrier(self):
+    if self.local is not None:
+      self.local.barrier()
+    if self.inter is not None and self.hosts > 1:
+      if self.device.type == "cuda":
+        self._dist.barrier(group=self.inter, device_ids=[self.device.index or 0])
+      else:
+        self._dist.barrier(group=self.inter)
+
+  def close(self):
+    if self.local is not None:
+      self.local.close()
+    self.bufs.clear()

@@ -93,14 +93,53 @@ def symm_from_ctx(ctx, ranks=None):
   return symm.SymmComm(me, size, exchange, ctx.device)
 
 
+def hier_layout(hosts, rank):
+  """Two-level layout of worker ranks: ``hosts[r]`` is the host of rank r.  Returns
+  ``(local_ranks, local_index, inter_groups)`` - the ranks of ``rank``'s host, its position among
+  them, and for every local index k the ranks holding index k on each host (in first-seen host
+  order) - or None when the hosts do not all run the same number of workers."""
+  by_host = {}
+  for r, h in enumerate(hosts):
+    by_host.setdefault(h, []).append(r)
+  sizes = set(len(v) for v in by_host.values())
+  if len(sizes) != 1:
+    return None
+  per = sizes.pop()
+  mine = by_host[hosts[rank]]
+  inter = [[by_host[h][k] for h in by_host] for k in range(per)]
+  return mine, mine.index(rank), inter
+
+
 def gradient_comm_from_ctx(ctx):
-  """SymmComm on one host, GroupComm (torch.distributed) across hosts or without a GPU;
-  ``TFOS_GRADIENT_COMM=group`` forces the latter (e.g. GPUs of one host without P2P access)."""
+  """The communicator a trainer's fused optimizer runs on:
+
+    * every worker on one host with a GPU  -> SymmComm (P2P / NVLS kernels, parallel/symm.py);
+    * several hosts with the same number of GPU workers each -> group_comm.HierComm (NVLink
+      reduce-scatter / all-gather kernels inside the host, NCCL between the hosts on the shards);
+    * anything else (uneven hosts, no GPU) -> group_comm.GroupComm (flat torch.distributed).
+
+  ``TFOS_GRADIENT_COMM=group`` forces the flat fallback (e.g. GPUs of one host without P2P
+  access), ``=hier`` insists on the two-level path (raises when the hosts are uneven)."""
   import torch
   force = os.environ.get("TFOS_GRADIENT_COMM", "auto")
   use_cuda = bool(ctx.gpus) and torch.cuda.is_available()
-  if force != "group" and use_cuda and ctx.single_host:
+  if force not in ("group", "hier") and use_cuda and ctx.single_host:
     return symm_from_ctx(ctx)
   from . import group_comm
   init_from_ctx(ctx)
-  return group_comm.GroupComm(device=ctx.device)
+  layout = hier_layout(ctx.worker_hosts(), ctx.rank) if (use_cuda and force != "group") else None
+  if layout is None:
+    if force == "hier":
+      raise RuntimeError("TFOS_GRADIENT_COMM=hier needs GPU workers, the same number on every host; "
+                         "hosts: {}".format(ctx.worker_hosts()))
+    return group_comm.GroupComm(device=ctx.device)
+  import torch.distributed as dist
+  mine, index, inter_groups = layout
+  inter = None
+  for k, ranks in enumerate(inter_groups):      # collective: every rank creates every group
+    g = dist.new_group(ranks=ranks) if len(ranks) > 1 else None
+    if k == index:
+      inter = g
+  local = symm_from_ctx(ctx, ranks=mine) if len(mine) > 1 else None
+  return group_comm.HierComm(local, inter, ctx.rank, ctx.world_size, device=ctx.device,
+                             local_rank=index, local_world=len(mine))

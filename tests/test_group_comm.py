@@ -34,6 +34,7 @@ class _KernelTwin(object):
   def allreduce_opt(self, d):
     st, o = self.store, self.optim
     assert d["world"] == 1 and d["grads"] == [st.grads.data_ptr()]
+    assert d.get("phase", 0) == (2 if o.hier_mode else 0)   # one-GPU hosts: no reduce-scatter half
     self.calls += 1
     h = o.hyper
     b, e = d["begin"], d["end"]
@@ -49,7 +50,7 @@ class _KernelTwin(object):
       st.aux32[lo - st.decay_end:e - st.decay_end] = st.master[lo:e]
 
 
-def _rank_main(rank, world, port, q):
+def _rank_main(rank, world, port, q, mode="group"):
   try:
     import torch.distributed as dist
     from tensorflowonspark_b200 import ops
@@ -58,7 +59,11 @@ def _rank_main(rank, world, port, q):
     from tensorflowonspark_b200.parallel.fused_optim import FusedOptimizer
     dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{}".format(port), rank=rank,
                             world_size=world)
-    comm = group_comm.GroupComm(device="cpu")
+    if mode == "group":
+      comm = group_comm.GroupComm(device="cpu")
+    else:       # two "hosts" with one worker each: inter-host all-reduce + the PHASE 2 half only
+      comm = group_comm.HierComm(None, dist.group.WORLD, rank, world, device="cpu")
+      assert (comm.hosts, comm.local_world, comm.local_rank) == (2, 1, 0)
     st = engine.ParamStore()
     st.register("w1", (16, 8), True, engine.normal(0.1))
     st.register("w2", (8, 8), True, engine.normal(0.1))
@@ -71,7 +76,7 @@ def _rank_main(rank, world, port, q):
                          buckets=[(0, 128, "a"), (128, n, "b")])
     twin = _KernelTwin(st, opt)
     ops.K.allreduce_opt = twin.allreduce_opt
-    assert opt.group_mode and opt.world == 1 and opt.gworld == world
+    assert (opt.group_mode or opt.hier_mode) and opt.world == 1 and opt.gworld == world
     assert abs(float(opt.hyper[3]) - 1.0 / world) < 1e-7
     w0 = st.master.clone()
     gens = [torch.Generator().manual_seed(100 + r) for r in range(world)]
@@ -100,8 +105,9 @@ def _rank_main(rank, world, port, q):
     same = all(torch.equal(everyone[0], t) for t in everyone)
     opt.assemble()                                                      # no-op: state is replicated
     sd = opt.state_dict()
-    with pytest.raises(RuntimeError):
-      comm.peer_ptrs("weights")
+    if mode == "group":
+      with pytest.raises(RuntimeError):
+        comm.peer_ptrs("weights")
     comm.barrier()
     q.put((rank, err, same, float((sd["state1"] - ref_m).abs().max())))
     dist.destroy_process_group()
@@ -110,11 +116,12 @@ def _rank_main(rank, world, port, q):
     q.put((rank, traceback.format_exc(), False, None))
 
 
-def test_group_mode_allreduce_update_keeps_replicas_identical():
+@pytest.mark.parametrize("mode", ["group", "hier"])
+def test_group_mode_allreduce_update_keeps_replicas_identical(mode):
   world, port = 2, _free_port()
   mp = multiprocessing.get_context("spawn")
   q = mp.Queue()
-  procs = [mp.Process(target=_rank_main, args=(r, world, port, q)) for r in range(world)]
+  procs = [mp.Process(target=_rank_main, args=(r, world, port, q, mode)) for r in range(world)]
   for p in procs:
     p.start()
   out = [q.get(timeout=120) for _ in procs]
@@ -146,3 +153,11 @@ def test_ctx_reports_hosts_and_refuses_symmetric_memory_across_hosts(monkeypatch
     ctx.symmetric_comm(ranks=[1, 2])
   one = {"chief": ["10.0.0.1:4000"], "worker": ["10.0.0.1:4001"]}
   assert _ctx(one, "chief", 0).single_host
+
+
+def test_hier_layout_groups_ranks_by_host_and_local_index():
+  from tensorflowonspark_b200.parallel.process_group import hier_layout
+  assert hier_layout(["a", "a", "b", "b"], 2) == ([2, 3], 0, [[0, 2], [1, 3]])
+  assert hier_layout(["a", "b", "a", "b"], 3) == ([1, 3], 1, [[0, 1], [2, 3]])    # interleaved hosts
+  assert hier_layout(["a", "a", "b"], 0) is None                                 # uneven: flat fallback
+  assert hier_layout(["a", "a"], 1) == ([0, 1], 1, [[0], [1]])

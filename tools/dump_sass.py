@@ -25,8 +25,10 @@ KERNELS = [
     ("igemm_wgrad_128", r"igemm_wgrad_kernel<128>"),
     ("igemm_wgrad_wide", r"igemm_wgrad_wide_kernel"),
     ("igemm_wgrad_halo", r"igemm_wgrad_halo_kernel"),
-    ("allreduce_opt_momentum_nvls", r"allreduce_opt_kernel<1, true>"),
-    ("allreduce_opt_momentum_p2p", r"allreduce_opt_kernel<1, false>"),
+    ("allreduce_opt_momentum_nvls", r"allreduce_opt_kernel<1, true, 0>"),
+    ("allreduce_opt_momentum_p2p", r"allreduce_opt_kernel<1, false, 0>"),
+    ("allreduce_phase1_reduce_scatter", r"allreduce_opt_kernel<0, false, 1>"),
+    ("allreduce_phase2_momentum_update_allgather", r"allreduce_opt_kernel<1, false, 2>"),
     ("ps_apply_momentum", r"ps_apply_kernel<1>"),
     ("ps_push_slot", r"ps_push_slot_kernel"),
     ("ps_pull_model", r"ps_pull_model_kernel"),
