@@ -15,7 +15,9 @@ trainers use (``alloc`` / ``broadcast`` / ``barrier`` / ``world`` / ``rank``):
     replicas stay bit-identical because every rank applies the same reduced gradient;
   * buffers are ordinary device memory; ``broadcast`` is ``dist.broadcast`` from the chief.
 
-``ctx.gradient_comm()`` picks: one host -> SymmComm (P2P / NVLS kernels), several -> GroupComm.
+``ctx.gradient_comm()`` picks: one host -> SymmComm (P2P / NVLS kernels); several hosts with the
+same number of GPU workers -> HierComm (below: NVLink inside the host, NCCL between hosts on the
+shards); anything else -> GroupComm.
 """
 import logging
 
