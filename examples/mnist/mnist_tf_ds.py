@@ -24,13 +24,6 @@ def main_fun(args, ctx):
   from tensorflowonspark_b200 import TFNode, tfrecord
   from tensorflowonspark_b200.utils import checkpoint, data
 
-  def parse_tfos(rec):
-    ex = tfrecord.decode_example(rec)
-    image = np.asarray(ex["image"][1], dtype=np.uint8)
-    label = ex["label"][1]
-    label = int(np.argmax(label)) if len(label) > 1 else int(label[0])   # one-hot or index
-    return image, np.int64(label)
-
   def parse_tfds(rec):
     ex = tfrecord.decode_example(rec)
     image = data.decode_png_gray(ex["image"][1][0]).reshape(-1)
@@ -41,7 +34,10 @@ def main_fun(args, ctx):
   pattern = TFNode.local_path(ctx.absolute_path(args.images_labels))
   ds = data.TFRecordPipeline(pattern, epochs=args.epochs, shuffle_buffer=args.buffer_size,
                              seed=ctx.rank).shard(ctx.world_size, ctx.rank)
-  ds = ds.map(parse_tfds if args.data_format == "tfds" else parse_tfos).batch(args.batch_size)
+  if args.data_format == "tfds":      # PNG-encoded images: decoded record by record
+    ds = ds.map(parse_tfds).batch(args.batch_size)
+  else:                               # int64 pixel lists: whole batches decoded natively into arrays
+    ds = ds.decode({"image": ("int64", 784, np.uint8), "label": ("int64", 1)}).batch(args.batch_size)
   model_dir = TFNode.local_path(ctx.absolute_path(args.model_dir))
   # every rank must take the same number of collective steps: the executor with the fewest records
   # would end first ("Out of Range" in the reference), so the loop is bounded up front
@@ -51,7 +47,7 @@ def main_fun(args, ctx):
   for images, labels in ds:
     if step >= steps_per_epoch * args.epochs:
       break
-    loss = trainer.step(images, labels)
+    loss = trainer.step(images, labels.reshape(-1))
     step += 1
     timer.tick(step, loss, args.batch_size * ctx.world_size)
     if step % steps_per_epoch == 0 and ctx.is_chief:     # ModelCheckpoint(save_weights_only=True)

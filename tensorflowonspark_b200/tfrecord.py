@@ -233,3 +233,48 @@ def decode_example(data):
   if n is not None:
     return dict(n.example_decode(bytes(data)))
   return _py_decode(data)
+
+
+_OUT_DTYPES = {"bytes": "uint8", "float": "float32", "int64": "int64"}
+
+
+def decode_batch(records, spec, threads=None):
+  """N serialized Examples -> ``{name: ndarray [N, length]}`` without a python object per value.
+
+  ``spec``: ``{name: (kind, length)}`` or ``{name: (kind, length, dtype)}`` - kind 'int64' decodes
+  to int64 (default), int32 or uint8; 'float' to float32; 'bytes' (ONE value of exactly
+  ``length`` bytes, e.g. raw pixels) to uint8.  Every record must hold exactly ``length`` values
+  of every requested feature; other features are skipped without being materialised.  The native
+  decoder (csrc/tfrecord.cc: decode_batch) walks the wire format once, writes straight into the
+  arrays, releases the GIL and splits large batches over threads."""
+  import numpy as np
+  records = [r if isinstance(r, bytes) else bytes(r) for r in records]
+  norm = []
+  for name, s in spec.items():
+    kind, length = s[0], int(s[1])
+    dt = np.dtype(s[2]).name if len(s) > 2 and s[2] is not None else _OUT_DTYPES[kind]
+    norm.append((name, kind, length, dt))
+  n = _native()
+  if n is not None:
+    if threads is None:
+      threads = min(8, max(1, len(records) // 4096))   # threads pay off for large batches only
+    return dict(n.example_decode_batch(records, norm, int(threads)))
+  out = {name: np.empty((len(records), length), dtype=dt) for name, _, length, dt in norm}
+  for r, rec in enumerate(records):
+    ex = _py_decode(rec)
+    for name, kind, length, dt in norm:
+      if name not in ex:
+        raise RuntimeError("record {}: feature '{}' has no values, {} requested".format(r, name, length))
+      k, vals = ex[name]
+      if k != kind:
+        raise RuntimeError("feature '{}' has another type than requested".format(name))
+      if kind == "bytes":
+        if len(vals) != 1 or len(vals[0]) != length:
+          raise RuntimeError("bytes feature '{}' is not one value of the requested length".format(name))
+        out[name][r] = np.frombuffer(vals[0], dtype=np.uint8)
+      else:
+        if len(vals) != length:
+          raise RuntimeError("record {}: feature '{}' has {} values, {} requested".format(
+              r, name, len(vals), length))
+        out[name][r] = np.asarray(vals).astype(dt)
+  return out

@@ -7,6 +7,13 @@ This module offers the same chain as plain generators over the native TFRecord c
 
   ds = data.TFRecordPipeline(pattern, epochs=3, shuffle_buffer=10000, seed=rank)
   for images, labels in ds.shard(world, rank).map(parse).batch(64): ...
+
+``decode(spec)`` instead of ``map(fn)`` parses a whole batch of records natively into dense
+arrays (tfrecord.decode_batch: no python object per value, ~13x the per-record path on
+MNIST-shaped Examples):
+
+  spec = {"image": ("int64", 784, "uint8"), "label": ("int64", 1)}
+  for images, labels in ds.decode(spec).batch(64): ...       # uint8 [64, 784], int64 [64, 1]
 """
 import glob
 import os
@@ -40,6 +47,7 @@ class TFRecordPipeline(object):
     self.seed, self.verify = seed, verify
     self._parse = None
     self._batch = None
+    self._spec = None
 
   def shard(self, num_shards, index):
     """Keep every ``num_shards``-th file (AutoShardPolicy.FILE); falls back to sharding by
@@ -53,6 +61,13 @@ class TFRecordPipeline(object):
 
   def map(self, fn):
     self._parse = fn
+    return self
+
+  def decode(self, spec, threads=None):
+    """Parse with the native batch decoder: ``spec`` = ``{feature: (kind, length[, dtype])}`` (see
+    :func:`tfrecord.decode_batch`); batches then are tuples of ``[n, length]`` arrays in the
+    order of ``spec``.  Needs :meth:`batch`; mutually exclusive with :meth:`map`."""
+    self._spec, self._threads = dict(spec), threads
     return self
 
   def batch(self, n, drop_remainder=True):
@@ -104,6 +119,22 @@ class TFRecordPipeline(object):
   def __iter__(self):
     import numpy as np
     it = self._shuffled(self._records())
+    if self._spec is not None:
+      if self._parse is not None or self._batch is None:
+        raise ValueError("decode(spec) replaces map(fn) and needs batch(n)")
+      n, drop = self._batch
+      names = list(self._spec)
+      rows = []
+      for rec in it:
+        rows.append(rec)
+        if len(rows) == n:
+          cols = tfrecord.decode_batch(rows, self._spec, self._threads)
+          yield tuple(cols[k] for k in names)
+          rows = []
+      if rows and not drop:
+        cols = tfrecord.decode_batch(rows, self._spec, self._threads)
+        yield tuple(cols[k] for k in names)
+      return
     if self._parse is not None:
       it = (self._parse(r) for r in it)
     if self._batch is None:

@@ -145,3 +145,75 @@ def test_tfrecord_pipeline_interleave_shuffle_shard_batch(tmp_path):
   assert len(batches) == 10 and batches[0][0].shape == (10,) and batches[0][1].shape == (10, 2)
   tail = list(data.TFRecordPipeline(pat).map(parse).batch(10, drop_remainder=False))
   assert len(tail) == 11 and tail[-1][0].shape == (3,)
+
+
+def _batch_examples(n=300, seed=0):
+  import numpy as np
+  rng = np.random.RandomState(seed)
+  img = rng.randint(0, 255, (n, 784))
+  big = rng.randint(-2 ** 62, 2 ** 62, (n, 3))            # ten-byte varints, negative values
+  big[0] = [-1, -2 ** 63, 2 ** 63 - 1]
+  big[1] = [127, 128, 16384]                               # the one / two / three byte boundaries
+  flt = rng.randn(n, 5).astype(np.float32)
+  raw = rng.randint(0, 256, (n, 12)).astype(np.uint8)
+  recs = [tfrecord.encode_example({
+      "image": ("int64", img[i].tolist()), "id": ("int64", big[i].tolist()),
+      "f": ("float", flt[i].tolist()), "raw": ("bytes", [raw[i].tobytes()]),
+      "unused": ("bytes", [b"skip me"])}) for i in range(n)]
+  return recs, img, big, flt, raw
+
+
+def test_decode_batch_writes_dense_arrays_and_agrees_with_the_python_twin():
+  import numpy as np
+  recs, img, big, flt, raw = _batch_examples()
+  spec = {"image": ("int64", 784, np.uint8), "id": ("int64", 3), "f": ("float", 5), "raw": ("bytes", 12)}
+  for threads in (1, 3):
+    out = tfrecord.decode_batch(recs, spec, threads=threads)
+    assert [out[k].dtype.name for k in spec] == ["uint8", "int64", "float32", "uint8"]
+    assert np.array_equal(out["image"], img.astype(np.uint8)) and np.array_equal(out["id"], big)
+    assert np.array_equal(out["f"], flt) and np.array_equal(out["raw"], raw)
+  as32 = tfrecord.decode_batch(recs[:7], {"image": ("int64", 784, "int32")})["image"]
+  assert as32.dtype == np.int32 and np.array_equal(as32, img[:7])
+  native, tfrecord._native = tfrecord._native, lambda: None      # the pure-python twin
+  try:
+    twin = tfrecord.decode_batch(recs[:20], spec)
+  finally:
+    tfrecord._native = native
+  full = tfrecord.decode_batch(recs[:20], spec)
+  assert all(np.array_equal(twin[k], full[k]) for k in spec)
+  assert tfrecord.decode_batch([], spec)["image"].shape == (0, 784)
+
+
+def test_decode_batch_rejects_records_that_do_not_match_the_spec():
+  recs, _, _, _, _ = _batch_examples(4)
+  for bad, msg in (({"image": ("int64", 100)}, "more values"), ({"image": ("int64", 785)}, "784 values"),
+                   ({"nope": ("int64", 1)}, "no values"), ({"f": ("int64", 5)}, "another type"),
+                   ({"raw": ("bytes", 11)}, "requested length")):
+    with pytest.raises(RuntimeError, match=msg):
+      tfrecord.decode_batch(recs, bad)
+  with pytest.raises(RuntimeError):
+    tfrecord.decode_batch([recs[0][:40]], {"image": ("int64", 784)})     # truncated record
+
+
+def test_pipeline_decode_stage_yields_the_same_batches_as_map(tmp_path):
+  import numpy as np
+  from tensorflowonspark_b200.utils import data
+  recs, img, _, _, _ = _batch_examples(100)
+  labelled = [tfrecord.encode_example({"image": ("int64", img[i].tolist()), "label": ("int64", [i % 10])})
+              for i in range(100)]
+  for k in range(2):
+    tfrecord.write_records(str(tmp_path / "part-{:05d}".format(k)), labelled[k * 50:(k + 1) * 50])
+
+  def parse(rec):
+    ex = tfrecord.decode_example(rec)
+    return np.asarray(ex["image"][1], dtype=np.uint8), np.asarray(ex["label"][1], dtype=np.int64)
+
+  def make():
+    return data.TFRecordPipeline(str(tmp_path), epochs=2, shuffle_buffer=16, seed=3)
+  slow = list(make().map(parse).batch(32, drop_remainder=False))
+  fast = list(make().decode({"image": ("int64", 784, np.uint8), "label": ("int64", 1)}).batch(32, drop_remainder=False))
+  assert len(slow) == len(fast) == 7 and fast[-1][0].shape == (8, 784)
+  for (a, b), (c, d) in zip(slow, fast):
+    assert np.array_equal(a, c) and np.array_equal(b, d)
+  with pytest.raises(ValueError):
+    list(make().decode({"label": ("int64", 1)}))                        # decode needs batch
