@@ -3,7 +3,7 @@ feeder tasks -> shared-memory ring -> DataFeed.next_batch_arrays on the node.  R
 segmentation example's (uint8 image [128,128,3], uint8 mask [128,128]) = 64 KiB each, produced
 without a random generator so that the producer is not the bottleneck.
 
-  python tools/bench_feed.py --executors 2 --examples 16384
+  python tools/bench_feed.py --executors 2 --examples 98304
 """
 import argparse
 import json
@@ -45,7 +45,7 @@ def main_fun(args, ctx):
 if __name__ == "__main__":
   p = argparse.ArgumentParser()
   p.add_argument("--executors", type=int, default=2)
-  p.add_argument("--examples", type=int, default=16384)
+  p.add_argument("--examples", type=int, default=98304)   # long enough for the ring slots to be warm
   p.add_argument("--batch", type=int, default=64)
   a = p.parse_args()
   from tensorflowonspark_b200 import TFCluster
