@@ -63,3 +63,21 @@ def test_spark_bootstrap_lockstep():
                      capture_output=True, text=True, timeout=600, cwd=root)
   print(p.stdout[-3000:], p.stderr[-2000:])
   assert p.returncode == 0 and "LOCKSTEP OK" in p.stdout
+
+
+def test_two_level_allreduce_halves_and_inter_host_step():
+  """Several-hosts path on the GPUs of one box (tools/gpu_check_hier.py): the fused kernel's
+  PHASE 1 / PHASE 2 halves ("1 host x N GPUs"), NCCL between one-GPU "hosts", and with 4+ GPUs
+  both levels at once - against torch.distributed.all_reduce + the update in PyTorch."""
+  import torch
+  n = torch.cuda.device_count()
+  if n < 2:
+    pytest.skip("needs 2 GPUs")
+  ranks = 4 if n >= 4 else 2
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node",
+                      str(ranks), "--master-addr", "127.0.0.1", "--master-port", _free_port(),
+                      os.path.join(root, "tools", "gpu_check_hier.py")],
+                     capture_output=True, text=True, timeout=600, cwd=root)
+  print(p.stdout[-4000:], p.stderr[-2000:])
+  assert p.returncode == 0 and "HIER CHECK PASSED" in p.stdout
