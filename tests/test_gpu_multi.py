@@ -67,13 +67,13 @@ def test_spark_bootstrap_lockstep():
 
 def test_two_level_allreduce_halves_and_inter_host_step():
   """Several-hosts path on the GPUs of one box (tools/gpu_check_hier.py): the fused kernel's
-  PHASE 1 / PHASE 2 halves ("1 host x N GPUs"), NCCL between one-GPU "hosts", and with 4+ GPUs
-  both levels at once - against torch.distributed.all_reduce + the update in PyTorch."""
+  PHASE 1 / PHASE 2 halves ("1 host x 2 GPUs") and NCCL between one-GPU "hosts" - against
+  torch.distributed.all_reduce + the update in PyTorch.  (Run the tool with 4 ranks by hand for
+  the "2 hosts x 2 GPUs" case; it is not part of the tier because it has not been run yet.)"""
   import torch
-  n = torch.cuda.device_count()
-  if n < 2:
+  if torch.cuda.device_count() < 2:
     pytest.skip("needs 2 GPUs")
-  ranks = 4 if n >= 4 else 2
+  ranks = 2
   root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
   p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node",
                       str(ranks), "--master-addr", "127.0.0.1", "--master-port", _free_port(),
