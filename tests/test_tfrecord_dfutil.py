@@ -217,3 +217,41 @@ def test_pipeline_decode_stage_yields_the_same_batches_as_map(tmp_path):
     assert np.array_equal(a, c) and np.array_equal(b, d)
   with pytest.raises(ValueError):
     list(make().decode({"label": ("int64", 1)}))                        # decode needs batch
+
+
+def test_mutated_records_decode_or_raise_never_crash():
+  """Untrusted bytes reach native parsers (csrc/tfrecord.cc): bit flips, truncation and splices
+  must end in a decoded value or a RuntimeError (tools/fuzz_tfrecord.sh runs the same loop under
+  AddressSanitizer + UBSan)."""
+  import random
+  rng = random.Random(7)
+  base = [tfrecord.encode_example({"image": ("int64", [rng.randrange(0, 70000) for _ in range(50)]),
+                                   "f": ("float", [1.0, 2.0, 3.0]), "raw": ("bytes", [bytes(range(16))]),
+                                   "label": ("int64", [3])}) for _ in range(4)]
+  spec = {"image": ("int64", 50, "int32"), "f": ("float", 3), "raw": ("bytes", 16), "label": ("int64", 1)}
+  decoded = rejected = 0
+  for it in range(3000):
+    recs = list(base)
+    i = rng.randrange(len(recs))
+    b = bytearray(recs[i])
+    m = rng.random()
+    if m < 0.5:
+      for _ in range(rng.randrange(1, 4)):
+        b[rng.randrange(len(b))] = rng.randrange(256)
+    elif m < 0.8:
+      del b[rng.randrange(len(b)):]
+    else:
+      p = rng.randrange(len(b))
+      b[p:p] = bytes(rng.randrange(256) for _ in range(rng.randrange(1, 9)))
+    recs[i] = bytes(b)
+    try:
+      out = tfrecord.decode_batch(recs, spec, threads=1)
+      assert out["image"].shape == (4, 50)
+      decoded += 1
+    except RuntimeError:
+      rejected += 1
+    try:
+      tfrecord.decode_example(recs[i])
+    except (RuntimeError, ValueError, UnicodeDecodeError):
+      pass
+  assert decoded > 0 and rejected > 0
