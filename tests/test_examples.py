@@ -97,3 +97,20 @@ def test_estimator_tf_mode_with_evaluator_sidecar_and_event_files(mnist):
   (eval_events,) = summary.event_files(md + "/eval")
   acc = [e["scalars"]["accuracy"] for e in summary.read_events(eval_events) if e["scalars"]]
   assert len(acc) == len(evals) and abs(acc[-1] - float(evals[-1][2])) < 1e-5
+
+
+def test_restart_from_checkpoint_after_an_injected_rank_failure(mnist):
+  """SURVEY 5.3 / 5.4 recovery story: a rank raises mid-training, TFCluster.shutdown leaves the
+  driver with an error, utils.recovery.run_with_restarts brings the job up again on a fresh
+  context and the nodes resume from the newest complete checkpoint (not from step 0)."""
+  md = mnist + "/model_resilient"
+  out = _run(["examples/mnist/mnist_resilient.py", "--cluster_size", "2", "--images_labels",
+              mnist + "/data/tfr", "--model_dir", md, "--max_steps", "60", "--save_steps", "10",
+              "--inject", "raise:rank=1:step=25"])
+  assert "injected fault on rank 1 at step 25" in out and "attempt 1 failed" in out
+  assert "chief:0 starts at step 0" in out and "chief:0 starts at step 20" in out
+  assert "worker:0 starts at step 20" in out             # every rank restores the same file
+  assert "job finished after 2 attempt(s)" in out
+  from tensorflowonspark_b200.utils import checkpoint
+  step, _ = checkpoint.load(md)
+  assert step == 60

@@ -232,3 +232,42 @@ def test_resnet50_comm_buckets_tile_the_parameter_vector():
   assert all(cov[i][1] == cov[i + 1][0] for i in range(len(cov) - 1))
   tail = sum(e - b for b, e, tag in buckets if tag == "stem")
   assert tail < 0.011 * st.total, tail      # ~1 % of the parameters are left for the tail
+
+
+def test_run_with_restarts_retries_on_a_fresh_context_and_gives_up_eventually():
+  from tensorflowonspark_b200.utils import recovery
+
+  class Ctx(object):
+    made = []
+
+    def __init__(self):
+      self.stopped = self.cancelled = 0
+      Ctx.made.append(self)
+
+    def stop(self):
+      self.stopped += 1
+
+    def cancelAllJobs(self):
+      self.cancelled += 1
+
+  seen, hooks = [], []
+
+  def job(sc, attempt):
+    seen.append((sc, attempt))
+    if attempt == 0:
+      raise SystemExit(1)          # how TFCluster.shutdown leaves a failed application
+    if attempt == 1:
+      raise RuntimeError("node lost")
+
+  n = recovery.run_with_restarts(Ctx, job, max_restarts=3, backoff_s=0.0,
+                                 on_failure=lambda a, e: hooks.append((a, type(e).__name__)))
+  assert n == 3 and [a for _, a in seen] == [0, 1, 2]
+  assert len({id(sc) for sc, _ in seen}) == 3                      # a new context per attempt
+  assert hooks == [(0, "SystemExit"), (1, "RuntimeError")]
+  assert all(c.stopped >= 1 for c in Ctx.made) and Ctx.made[0].cancelled == 1 and Ctx.made[2].cancelled == 0
+
+  with pytest.raises(recovery.JobFailed) as info:
+    recovery.run_with_restarts(Ctx, lambda sc, a: (_ for _ in ()).throw(ValueError(a)), max_restarts=1, backoff_s=0.0)
+  assert [type(c).__name__ for c in info.value.causes] == ["ValueError", "ValueError"]
+  with pytest.raises(KeyboardInterrupt):                           # never swallowed
+    recovery.run_with_restarts(Ctx, lambda sc, a: (_ for _ in ()).throw(KeyboardInterrupt()), backoff_s=0.0)
