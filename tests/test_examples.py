@@ -114,3 +114,36 @@ def test_restart_from_checkpoint_after_an_injected_rank_failure(mnist):
   from tensorflowonspark_b200.utils import checkpoint
   step, _ = checkpoint.load(md)
   assert step == 60
+
+
+def test_streaming_feed_with_async_parameter_server_stops_on_terminate(mnist, tmp_path):
+  """reference examples/mnist/estimator/mnist_spark_streaming.py: DStream micro-batches feed one
+  worker, parameters live on a ps node and are updated without barriers; the worker's
+  ``terminate()`` reaches the driver through the reservation server and ``shutdown(ssc)`` ends
+  the stream."""
+  import shutil
+  import time
+  watched = tmp_path / "stream"
+  watched.mkdir()
+  log = open(str(tmp_path / "out.log"), "w")
+  env = dict(os.environ, CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="2")
+  p = subprocess.Popen([sys.executable, "examples/mnist/mnist_spark_streaming.py", "--cluster_size", "2",
+                        "--images_labels", str(watched), "--max_examples", "256", "--interval", "0.3"],
+                       cwd=ROOT, env=env, stdout=log, stderr=subprocess.STDOUT)
+  try:
+    time.sleep(5)                                        # cluster up, stream started
+    parts = sorted(f for f in os.listdir(mnist + "/data/csv/train") if f.startswith("part-"))
+    for i, name in enumerate(parts):                     # files appearing in the watched directory
+      if p.poll() is not None:
+        break
+      shutil.copy(os.path.join(mnist, "data/csv/train", name), str(watched / "f{}.csv".format(i)))
+      time.sleep(1)
+    rc = p.wait(timeout=120)
+  finally:
+    if p.poll() is None:
+      p.kill()
+    log.close()
+  out = open(str(tmp_path / "out.log")).read()
+  assert rc == 0, out[-3000:]
+  assert "terminate() invoked" in out and "server done, stopping the StreamingContext" in out
+  assert "slot mode" not in out and "serving parameters" in out          # plain (Hogwild) ps node
