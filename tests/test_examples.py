@@ -147,3 +147,25 @@ def test_streaming_feed_with_async_parameter_server_stops_on_terminate(mnist, tm
   assert rc == 0, out[-3000:]
   assert "terminate() invoked" in out and "server done, stopping the StreamingContext" in out
   assert "slot mode" not in out and "serving parameters" in out          # plain (Hogwild) ps node
+
+
+def test_remaining_mnist_drivers_tf_mode_and_estimator_spark_mode(mnist):
+  """examples/mnist/mnist_tf.py (InputMode.TENSORFLOW, every worker reads its shard) and
+  estimator/mnist_spark.py (InputMode.SPARK, periodic checkpoints, terminate() on max steps)
+  followed by estimator/mnist_inference.py (foreachPartition with a per-executor model cache) -
+  reference examples/mnist/keras/mnist_tf.py, estimator/mnist_spark.py, estimator/mnist_inference.py."""
+  _run(["examples/mnist/mnist_tf.py", "--cluster_size", "2", "--images_labels", mnist + "/data/tfr/train",
+        "--num_examples", "2048", "--epochs", "2", "--batch_size", "32", "--learning_rate", "0.05",
+        "--export_dir", mnist + "/export_tf"])
+  assert os.path.exists(mnist + "/export_tf/signature.json")
+  _run(["examples/mnist/estimator/mnist_spark.py", "--cluster_size", "2", "--images_labels",
+        mnist + "/data/csv/train", "--num_examples", "2048", "--epochs", "2", "--batch_size", "32",
+        "--learning_rate", "0.05", "--model_dir", mnist + "/model_es", "--export_dir", mnist + "/export_es"])
+  from tensorflowonspark_b200.utils import checkpoint
+  step, _ = checkpoint.load(mnist + "/model_es")
+  assert step >= 50                                       # 90 % of 2048 * 2 / (32 * 2) collective steps
+  for export in ("/export_tf", "/export_es"):
+    out = _run(["examples/mnist/estimator/mnist_inference.py", "--cluster_size", "2", "--images_labels",
+                mnist + "/data/tfr/test", "--export_dir", mnist + export, "--output",
+                mnist + "/pred" + export.replace("/", "_")])
+    assert float(re.search(r"accuracy: ([\d.]+)", out).group(1)) > 0.3
