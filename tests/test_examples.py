@@ -169,3 +169,16 @@ def test_remaining_mnist_drivers_tf_mode_and_estimator_spark_mode(mnist):
                 mnist + "/data/tfr/test", "--export_dir", mnist + export, "--output",
                 mnist + "/pred" + export.replace("/", "_")])
     assert float(re.search(r"accuracy: ([\d.]+)", out).group(1)) > 0.3
+
+
+def test_keras_style_ml_pipeline_and_the_cli_helpers(mnist):
+  """examples/mnist/mnist_pipeline.py (TFEstimator.fit -> TFModel.transform + argmax, reference
+  examples/mnist/keras/mnist_pipeline.py:120-146) and examples/utils/mnist_reshape.py."""
+  import json
+  out = _run(["examples/mnist/mnist_pipeline.py", "--cluster_size", "2", "--images_labels",
+              mnist + "/data/csv/train", "--epochs", "1", "--batch_size", "32", "--learning_rate", "0.05",
+              "--export_dir", mnist + "/export_pipe"])
+  assert float(re.search(r"pipeline accuracy on \d+ rows: ([\d.]+)", out).group(1)) > 0.3
+  row = ",".join(["7"] + [str(i % 256) for i in range(784)])
+  shaped = json.loads(_run(["examples/utils/mnist_reshape.py", row]).strip().splitlines()[-1])
+  assert shaped["label"] == 7 and len(shaped["image"]) == 28 and shaped["image"][1][0] == 28
