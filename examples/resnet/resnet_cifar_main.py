@@ -149,6 +149,8 @@ class LocalContext(object):
   def symmetric_comm(self):
     return self._comm
 
+  gradient_comm = symmetric_comm     # (one host under torchrun: always the peer-mapped communicator)
+
 
 if __name__ == "__main__":
   main_fun(sys.argv, LocalContext())
