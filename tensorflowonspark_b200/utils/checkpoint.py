@@ -12,12 +12,15 @@ Here:
 * ``export_model`` / ``load_model`` - ``export_dir/{weights.pt, signature.json}``; the JSON keeps
   the meaning of the pipeline params ``signature_def_key`` / ``tag_set`` / input & output
   mappings (tensorflowonspark/pipeline.py:244-296).
+
+Every path may name a remote filesystem (``hdfs://``, ``s3://`` ...; utils/fs.py), as
+``ctx.absolute_path(model_dir)`` produces on a cluster whose ``defaultFS`` is not local.
 """
 import json
 import logging
-import os
 import re
-import tempfile
+
+from . import fs
 
 logger = logging.getLogger(__name__)
 
@@ -25,47 +28,39 @@ INDEX = "checkpoint"
 
 
 def _local(path):
-  return path[len("file://"):] if path.startswith("file://") else path
+  return fs.local(path) if fs.is_local(path) else str(path)
 
 
 def _atomic_torch_save(obj, path):
   import torch
-  d = os.path.dirname(path) or "."
-  os.makedirs(d, exist_ok=True)
-  fd, tmp = tempfile.mkstemp(dir=d, prefix=".tmp-", suffix=".pt")
-  try:
-    with os.fdopen(fd, "wb") as f:
-      torch.save(obj, f)
-      f.flush()
-      os.fsync(f.fileno())
-    os.replace(tmp, path)
-  except Exception:
-    if os.path.exists(tmp):
-      os.remove(tmp)
-    raise
+  fs.write_atomic(path, lambda f: torch.save(obj, f))
+
+
+def _torch_load(path, map_location):
+  import torch
+  with fs.open_read(path) as f:
+    return torch.load(f, map_location=map_location, weights_only=False)
 
 
 def save(model_dir, step, state, keep=5, model=None, signatures=None):
   """Write ``state`` (any picklable / tensor dict) as checkpoint ``step``; prune old ones.
 
-  ``model`` (optional): the object the state came from.  Its ``export_builder`` is recorded in
-  ``model_dir/signature.json`` so that the newest checkpoint can be *served* without an export
-  (``load_model_dir``; the reference's TFModel falls back to ``tf.train.latest_checkpoint(
-  model_dir)`` when no ``export_dir`` is given, pipeline.py:549-555)."""
+  ``model_dir`` may live on any filesystem ``utils/fs.py`` resolves (plain / ``file://`` paths,
+  ``hdfs://``, ``s3://`` ...).  ``model`` (optional): the object the state came from.  Its
+  ``export_builder`` is recorded in ``model_dir/signature.json`` so that the newest checkpoint can
+  be *served* without an export (``load_model_dir``; the reference's TFModel falls back to
+  ``tf.train.latest_checkpoint(model_dir)`` when no ``export_dir`` is given, pipeline.py:549-555)."""
   model_dir = _local(model_dir)
-  path = os.path.join(model_dir, "ckpt-{:08d}.pt".format(int(step)))
+  path = fs.join(model_dir, "ckpt-{:08d}.pt".format(int(step)))
   _atomic_torch_save({"step": int(step), "state": state}, path)
   if model is not None and getattr(model, "export_builder", None):
     _write_signature(model_dir, model, "serve", signatures)
-  tmp = os.path.join(model_dir, "." + INDEX + ".tmp")
-  with open(tmp, "w") as f:
-    json.dump({"latest": os.path.basename(path), "step": int(step)}, f)
-  os.replace(tmp, os.path.join(model_dir, INDEX))
-  ckpts = sorted(f for f in os.listdir(model_dir) if re.match(r"ckpt-\d+\.pt$", f))
+  fs.write_text(fs.join(model_dir, INDEX), json.dumps({"latest": fs.basename(path), "step": int(step)}))
+  ckpts = sorted(f for f in fs.listdir(model_dir) if re.match(r"ckpt-\d+\.pt$", f))
   for old in ckpts[:-keep] if keep else []:
     try:
-      os.remove(os.path.join(model_dir, old))
-    except OSError:
+      fs.remove(fs.join(model_dir, old))
+    except (OSError, IOError):
       pass
   return path
 
@@ -73,30 +68,28 @@ def save(model_dir, step, state, keep=5, model=None, signatures=None):
 def latest_checkpoint(model_dir):
   """Path of the newest complete checkpoint in ``model_dir`` or None."""
   model_dir = _local(model_dir)
-  if not os.path.isdir(model_dir):
+  if not fs.isdir(model_dir):
     return None
-  idx = os.path.join(model_dir, INDEX)
-  if os.path.exists(idx):
+  idx = fs.join(model_dir, INDEX)
+  if fs.exists(idx):
     try:
-      with open(idx) as f:
-        p = os.path.join(model_dir, json.load(f)["latest"])
-      if os.path.exists(p):
+      p = fs.join(model_dir, json.loads(fs.read_text(idx))["latest"])
+      if fs.exists(p):
         return p
     except Exception:
       pass
-  ckpts = sorted(f for f in os.listdir(model_dir) if re.match(r"ckpt-\d+\.pt$", f))
-  return os.path.join(model_dir, ckpts[-1]) if ckpts else None
+  ckpts = sorted(f for f in fs.listdir(model_dir) if re.match(r"ckpt-\d+\.pt$", f))
+  return fs.join(model_dir, ckpts[-1]) if ckpts else None
 
 
 def load(path_or_dir, map_location="cpu"):
   """(step, state) of a checkpoint file, or of the latest one in a directory; (0, None) if none."""
-  import torch
   p = _local(path_or_dir)
-  if os.path.isdir(p):
+  if fs.isdir(p):
     p = latest_checkpoint(p)
-  if not p or not os.path.exists(p):
+  if not p or not fs.exists(p):
     return 0, None
-  blob = torch.load(p, map_location=map_location, weights_only=False)
+  blob = _torch_load(p, map_location)
   return blob["step"], blob["state"]
 
 
@@ -116,10 +109,7 @@ def _write_signature(directory, model, tag_set, signatures, builder=None):
       "builder": builder or getattr(model, "export_builder", None),
       "builder_args": getattr(model, "export_builder_args", {}),
   }
-  tmp = os.path.join(directory, ".signature.tmp")
-  with open(tmp, "w") as f:
-    json.dump(sig, f, indent=1)
-  os.replace(tmp, os.path.join(directory, "signature.json"))
+  fs.write_text(fs.join(directory, "signature.json"), json.dumps(sig, indent=1))
   return sig
 
 
@@ -136,8 +126,8 @@ def export_model(model, export_dir, tag_set="serve", signatures=None, builder=No
       ``export_builder`` attribute when present.
   """
   export_dir = _local(export_dir)
-  os.makedirs(export_dir, exist_ok=True)
-  _atomic_torch_save(_state_of(model), os.path.join(export_dir, "weights.pt"))
+  fs.makedirs(export_dir)
+  _atomic_torch_save(_state_of(model), fs.join(export_dir, "weights.pt"))
   _write_signature(export_dir, model, tag_set, signatures, builder)
   logger.info("exported model to %s", export_dir)
   return export_dir
@@ -156,15 +146,14 @@ def load_model_dir(model_dir, map_location="cpu"):
   inference fallback when nothing was exported (reference pipeline.py:549-555).  Needs the
   ``signature.json`` that ``save(..., model=...)`` writes next to the checkpoints."""
   model_dir = _local(model_dir)
-  sig_path = os.path.join(model_dir, "signature.json")
+  sig_path = fs.join(model_dir, "signature.json")
   latest = latest_checkpoint(model_dir)
   if latest is None:
     raise IOError("no checkpoint found in model_dir {}".format(model_dir))
-  if not os.path.exists(sig_path):
+  if not fs.exists(sig_path):
     raise IOError("{} has checkpoints but no signature.json: save them with "
                   "checkpoint.save(..., model=<model>) to make them servable".format(model_dir))
-  with open(sig_path) as f:
-    sig = json.load(f)
+  sig = json.loads(fs.read_text(sig_path))
   _, state = load(latest, map_location)
   if isinstance(state, dict) and "model" in state and "optimizer" in state:
     state = state["model"]      # a training checkpoint: only the parameters are served
@@ -174,15 +163,12 @@ def load_model_dir(model_dir, map_location="cpu"):
 
 def load_model(export_dir, tag_set=None, map_location="cpu"):
   """(callable_or_state_dict, signature_json) from an exported artefact."""
-  import torch
   export_dir = _local(export_dir)
-  with open(os.path.join(export_dir, "signature.json")) as f:
-    sig = json.load(f)
+  sig = json.loads(fs.read_text(fs.join(export_dir, "signature.json")))
   if tag_set:
     want = tag_set if isinstance(tag_set, (list, tuple)) else str(tag_set).split(",")
     if not set(want) <= set(sig["tag_set"]):
       raise ValueError("export at {} has tags {}, requested {}".format(export_dir, sig["tag_set"],
                                                                        want))
-  state = torch.load(os.path.join(export_dir, "weights.pt"), map_location=map_location,
-                     weights_only=False)
+  state = _torch_load(fs.join(export_dir, "weights.pt"), map_location)
   return _build(sig, state), sig

@@ -118,19 +118,31 @@ class SummaryWriter(object):
   ``add_scalar`` per step; the file is touched a few times a minute).  Thread-safe."""
 
   def __init__(self, logdir, filename_suffix="", flush_secs=10.0, max_queue=64):
-    from .. import TFNode
-    logdir = TFNode.local_path(logdir) if "://" in str(logdir) else str(logdir)
-    os.makedirs(logdir, exist_ok=True)
+    from . import fs
     with _lock:
       _counter[0] += 1
       uid = _counter[0]
-    self.path = os.path.join(logdir, "events.out.tfevents.{:010d}.{}.{}.{}{}".format(
-        int(time.time()), socket.gethostname(), os.getpid(), uid, filename_suffix))
+    name = "events.out.tfevents.{:010d}.{}.{}.{}{}".format(
+        int(time.time()), socket.gethostname(), os.getpid(), uid, filename_suffix)
+    # a log directory on a remote filesystem (hdfs://, s3:// ... - utils/fs.py): records are
+    # appended to a local spool file which replaces the remote copy at every flush (event files
+    # of a training run are small, and TensorBoard re-reads them periodically anyway)
+    self.remote = None
+    if fs.is_local(logdir):
+      logdir = fs.local(logdir)
+      os.makedirs(logdir, exist_ok=True)
+    else:
+      import tempfile
+      fs.makedirs(logdir)
+      self.remote = fs.join(str(logdir), name)
+      logdir = tempfile.mkdtemp(prefix="tfos-events-")
+    self.path = os.path.join(logdir, name)
     self.flush_secs, self.max_queue = flush_secs, max_queue
     self._pending, self._last = [], time.time()
     self._mutex = threading.Lock()
     self._closed = False
     tfrecord.write_records(self.path, [_event(time.time(), file_version=_FILE_VERSION)])
+    self._upload()
 
   def _add(self, step, value, wall_time):
     with self._mutex:
@@ -160,6 +172,12 @@ class SummaryWriter(object):
       self._last = time.time()
       if batch:
         tfrecord.write_records(self.path, batch, append=True)
+        self._upload()
+
+  def _upload(self):
+    if self.remote is not None:
+      from . import fs
+      fs.copy_from_local(self.path, self.remote)
 
   def close(self):
     self.flush()

@@ -271,3 +271,48 @@ def test_run_with_restarts_retries_on_a_fresh_context_and_gives_up_eventually():
   assert [type(c).__name__ for c in info.value.causes] == ["ValueError", "ValueError"]
   with pytest.raises(KeyboardInterrupt):                           # never swallowed
     recovery.run_with_restarts(Ctx, lambda sc, a: (_ for _ in ()).throw(KeyboardInterrupt()), backoff_s=0.0)
+
+
+def test_checkpoints_exports_and_event_files_on_a_remote_filesystem():
+  """model_dir / export_dir / log_dir may be URIs of any filesystem pyarrow resolves (hdfs://,
+  s3:// ... - what ``ctx.absolute_path`` yields when the cluster's defaultFS is not local, and
+  what lets another host resume or serve what the chief wrote).  pyarrow's in-memory ``mock://``
+  filesystem stands in for the remote store."""
+  pytest.importorskip("pyarrow")
+  from tensorflowonspark_b200.models import simple
+  from tensorflowonspark_b200.utils import fs, summary
+  root = "mock:///jobs/run1"
+  md, ed = root + "/model", root + "/export"
+  assert not fs.is_local(md) and fs.is_local("file:///tmp/x") and fs.is_local("/tmp/x")
+  assert checkpoint.latest_checkpoint(md) is None and checkpoint.load(md) == (0, None)
+  model = simple.Linear(2, 1)
+  for step in (10, 20, 30, 40):
+    path = checkpoint.save(md, step, {"w": torch.full((4,), float(step))}, keep=2, model=model)
+  assert path == md + "/ckpt-00000040.pt" and checkpoint.latest_checkpoint(md) == path
+  names = sorted(fs.listdir(md))
+  assert names == ["checkpoint", "ckpt-00000030.pt", "ckpt-00000040.pt", "signature.json"]   # pruned, no temp files
+  step, state = checkpoint.load(md)
+  assert step == 40 and torch.equal(state["w"], torch.full((4,), 40.0))
+  assert checkpoint.load(md + "/ckpt-00000030.pt")[0] == 30
+  # export -> load_model, and serving the newest checkpoint of model_dir without an export
+  checkpoint.save(md, 50, model.state_dict(), model=model)
+  checkpoint.export_model(model, ed, signatures={"serving_default": {"inputs": {"x": "x"}, "outputs": {"y": "y"}}})
+  served, sig = checkpoint.load_model(ed, "serve")
+  x = torch.tensor([[1.0, 2.0]])
+  assert torch.allclose(served(x=x.numpy())["y"].cpu(), model(x).detach())
+  served2, _ = checkpoint.load_model_dir(md)
+  assert torch.allclose(served2(x=x.numpy())["y"].cpu(), model(x).detach())
+  with pytest.raises(ValueError):
+    checkpoint.load_model(ed, "other_tag")
+  # TensorBoard events: spooled locally, mirrored to the remote log directory at every flush
+  w = summary.SummaryWriter(md, flush_secs=1e9, max_queue=2)
+  w.add_scalar("loss", 1.0, 1)
+  w.add_scalar("loss", 0.5, 2)                 # second event reaches max_queue -> flush -> upload
+  (remote,) = [n for n in fs.listdir(md) if n.startswith("events.out.tfevents.")]
+  local_copy = os.path.join(os.path.dirname(w.path), "check")
+  with fs.open_read(md + "/" + remote) as src, open(local_copy, "wb") as dst:
+    dst.write(src.read())
+  assert [e["scalars"].get("loss") for e in summary.read_events(local_copy)] == [None, 1.0, 0.5]
+  w.close()
+  with pytest.raises(IOError, match="client library"):
+    checkpoint.save("nosuchscheme://host/dir", 1, {})
