@@ -46,8 +46,30 @@ def masked_crc32c(data):
   return (((crc >> 15) | (crc << 17)) + _MASK_DELTA) & 0xffffffff
 
 
+def _remote(path):
+  from .utils import fs
+  return None if fs.is_local(path) else fs
+
+
 def write_records(path, records, append=False):
+  """TFRecord file from an iterable of serialized records.  ``path`` may be a URI of a remote
+  filesystem (utils/fs.py): the file is then written locally and uploaded (no ``append``)."""
   records = [bytes(r) for r in records]
+  rfs = _remote(path)
+  if rfs is not None:
+    if append:
+      raise ValueError("cannot append to a TFRecord file on a remote filesystem: " + str(path))
+    import os
+    import tempfile
+    fd, tmp = tempfile.mkstemp(suffix=".tfrecord")
+    os.close(fd)
+    try:
+      write_records(tmp, records)
+      rfs.copy_from_local(tmp, path)
+    finally:
+      os.remove(tmp)
+    return None
+  path = path[len("file://"):] if str(path).startswith("file://") else path
   n = _native()
   if n is not None:
     return n.tfrecord_write(path, records, append)
@@ -61,27 +83,39 @@ def write_records(path, records, append=False):
 
 
 def read_records(path, verify=True):
+  """Records of one TFRecord file (CRCs checked unless ``verify=False``).  A URI of a remote
+  filesystem (``hdfs://`` ..., utils/fs.py) is streamed through that filesystem and framed here,
+  with the native CRC32C."""
+  rfs = _remote(path)
+  if rfs is not None:
+    with rfs.open_read(path) as f:
+      return _read_stream(f, verify, str(path))
+  path = path[len("file://"):] if str(path).startswith("file://") else path
   n = _native()
   if n is not None:
     return n.tfrecord_read(path, verify)
-  out = []
   with open(path, "rb") as f:
-    while True:
-      hdr = f.read(12)
-      if not hdr:
-        break
-      if len(hdr) != 12:
-        raise IOError("truncated TFRecord header in " + path)
-      (length,), (crc,) = struct.unpack("<Q", hdr[:8]), struct.unpack("<I", hdr[8:])
-      if verify and masked_crc32c(hdr[:8]) != crc:
-        raise IOError("corrupt TFRecord length CRC in " + path)
-      data = f.read(length)
-      tail = f.read(4)
-      if len(data) != length or len(tail) != 4:
-        raise IOError("truncated TFRecord payload in " + path)
-      if verify and masked_crc32c(data) != struct.unpack("<I", tail)[0]:
-        raise IOError("corrupt TFRecord data CRC in " + path)
-      out.append(data)
+    return _read_stream(f, verify, path)
+
+
+def _read_stream(f, verify, path):
+  out = []
+  while True:
+    hdr = f.read(12)
+    if not hdr:
+      break
+    if len(hdr) != 12:
+      raise IOError("truncated TFRecord header in " + path)
+    (length,), (crc,) = struct.unpack("<Q", hdr[:8]), struct.unpack("<I", hdr[8:])
+    if verify and masked_crc32c(hdr[:8]) != crc:
+      raise IOError("corrupt TFRecord length CRC in " + path)
+    data = f.read(length)
+    tail = f.read(4)
+    if len(data) != length or len(tail) != 4:
+      raise IOError("truncated TFRecord payload in " + path)
+    if verify and masked_crc32c(data) != struct.unpack("<I", tail)[0]:
+      raise IOError("corrupt TFRecord data CRC in " + path)
+    out.append(data)
   return out
 
 

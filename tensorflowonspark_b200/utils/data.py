@@ -23,14 +23,25 @@ from .. import tfrecord
 
 
 def list_files(pattern):
-  """Sorted files matching a glob pattern, a directory (its ``part-*`` files) or a comma list."""
+  """Sorted files matching a glob pattern, a directory (its ``part-*`` files) or a comma list;
+  plain / ``file://`` paths and URIs of remote filesystems (``hdfs://`` ..., utils/fs.py - there
+  the wildcard may only be in the file name)."""
+  import fnmatch
+  from . import fs
   out = []
   for piece in str(pattern).split(","):
-    piece = piece[len("file://"):] if piece.startswith("file://") else piece
-    if os.path.isdir(piece):
-      out.extend(sorted(glob.glob(os.path.join(piece, "part-*"))))
+    if fs.is_local(piece):
+      piece = fs.local(piece)
+      if os.path.isdir(piece):
+        out.extend(sorted(glob.glob(os.path.join(piece, "part-*"))))
+      else:
+        out.extend(sorted(glob.glob(piece)))
+    elif fs.isdir(piece):
+      out.extend(fs.join(piece, n) for n in sorted(fs.listdir(piece)) if n.startswith("part-"))
     else:
-      out.extend(sorted(glob.glob(piece)))
+      d, name = fs.dirname(piece), fs.basename(piece)
+      if fs.isdir(d):
+        out.extend(fs.join(d, n) for n in sorted(fs.listdir(d)) if fnmatch.fnmatch(n, name))
   return out
 
 

@@ -255,3 +255,36 @@ def test_mutated_records_decode_or_raise_never_crash():
     except (RuntimeError, ValueError, UnicodeDecodeError):
       pass
   assert decoded > 0 and rejected > 0
+
+
+def test_tfrecord_files_and_input_pipeline_on_a_remote_filesystem():
+  """InputMode.TENSORFLOW workers read their TFRecord shards from wherever the data lives - the
+  reference gets ``hdfs://`` from TensorFlow's filesystem layer (examples/mnist/keras/
+  mnist_tf_ds.py:41-50 with ``ctx.absolute_path``).  pyarrow's in-memory filesystem stands in."""
+  pytest.importorskip("pyarrow")
+  import numpy as np
+  from tensorflowonspark_b200.utils import data
+  base = "mock:///datasets/mnist/train"
+  recs = [tfrecord.encode_example({"image": ("int64", [i % 256] * 16), "label": ("int64", [i % 10])})
+          for i in range(60)]
+  for k in range(3):
+    tfrecord.write_records("{}/part-{:05d}".format(base, k), recs[k * 20:(k + 1) * 20])
+  tfrecord.write_records(base + "/_SUCCESS", [])
+  assert tfrecord.read_records(base + "/part-00001") == recs[20:40]
+  assert data.list_files(base) == [base + "/part-0000{}".format(k) for k in range(3)]
+  assert data.list_files(base + "/part-*1") == [base + "/part-00001"]
+  with pytest.raises(ValueError):
+    tfrecord.write_records(base + "/part-00000", recs[:1], append=True)
+  spec = {"image": ("int64", 16, np.uint8), "label": ("int64", 1)}
+  batches = list(data.TFRecordPipeline(base, epochs=1).shard(3, 1).decode(spec).batch(10))
+  assert len(batches) == 2                                   # one of the three files, 20 records
+  labels = np.concatenate([b[1].reshape(-1) for b in batches])
+  assert sorted(labels.tolist()) == sorted(i % 10 for i in range(20, 40))
+  # a flipped payload byte is caught by the CRC check on the remote path too
+  from tensorflowonspark_b200.utils import fs
+  with fs.open_read(base + "/part-00000") as f:
+    blob = bytearray(f.read())
+  blob[20] ^= 0xff
+  fs.write_atomic(base + "/corrupt", lambda f: f.write(bytes(blob)))
+  with pytest.raises(IOError, match="CRC"):
+    tfrecord.read_records(base + "/corrupt")
