@@ -29,6 +29,8 @@ def parse(argv):
   p.add_argument("--no_graph", action="store_true")
   p.add_argument("--tensorboard", action="store_true")
   p.add_argument("--metrics", default=None, help="JSONL file for per-step metrics")
+  p.add_argument("--metrics_port", type=int, default=None,
+                 help="serve the same fields on a Prometheus /metrics endpoint (port + rank; 0: any free port)")
   return p.parse_args(argv)
 
 
@@ -64,7 +66,11 @@ def main_fun(argv, ctx):
   net.train_step()
   if not args.no_graph:
     net.capture()
-  log = metrics.StepLogger(args.metrics, rank=ctx.rank) if args.metrics else None
+  exporter = None
+  if args.metrics_port is not None and metrics.Exporter.available():
+    exporter = metrics.Exporter(rank=ctx.rank, port=args.metrics_port + ctx.rank if args.metrics_port else 0)
+    print("rank {} metrics at {}".format(ctx.rank, exporter.url()))
+  log = metrics.StepLogger(args.metrics, rank=ctx.rank, exporter=exporter) if args.metrics else None
   events = None
   if args.model_dir and ctx.is_chief:     # TensorBoard scalars next to the checkpoints
     from tensorflowonspark_b200.utils import summary
@@ -86,6 +92,8 @@ def main_fun(argv, ctx):
         log.log(step=step + 1, loss=float(loss), images_per_s=rate, step_ms=dt * 100)
       if events:
         events.add_scalars({"loss": float(loss), "images_per_s": rate}, step + 1)
+      if exporter and not log:
+        exporter.update(step=step + 1, loss=float(loss), images_per_s=rate, step_ms=dt * 100)
       t0 = time.time()
     if args.model_dir and args.save_steps and (step + 1) % args.save_steps == 0 and ctx.is_chief:
       checkpoint.save(ctx.absolute_path(args.model_dir), step + 1,
@@ -93,6 +101,8 @@ def main_fun(argv, ctx):
   torch.cuda.synchronize()
   if events:
     events.close()
+  if exporter:
+    exporter.close()
 
 
 if __name__ == "__main__":

@@ -101,7 +101,7 @@ def test_resnet_spark_driver_checkpoints_metrics_events_and_resume(fake_gpu, tmp
   mod = importlib.import_module("resnet_spark")
   md, mt = str(tmp_path / "ckpt"), str(tmp_path / "steps.jsonl")
   argv = ["resnet_spark.py", "--batch_size", "8", "--image", "64", "--train_steps", "25", "--model_dir", md,
-          "--save_steps", "10", "--metrics", mt, "--epochs_per_step", "10"]
+          "--save_steps", "10", "--metrics", mt, "--epochs_per_step", "10", "--metrics_port", "0"]
   mod.main_fun(argv, _Ctx())
   net = _Trainer.made[-1]
   assert net.kw["depth"] == 50 and net.kw["batch"] == 8 and net.kw["comm"] is None and net.captured

@@ -316,3 +316,23 @@ def test_checkpoints_exports_and_event_files_on_a_remote_filesystem():
   w.close()
   with pytest.raises(IOError, match="client library"):
     checkpoint.save("nosuchscheme://host/dir", 1, {})
+
+
+def test_prometheus_exporter_serves_what_the_step_logger_logs(tmp_path):
+  import urllib.request
+  if not metrics.Exporter.available():
+    pytest.skip("prometheus_client not installed")
+  exp = metrics.Exporter(rank=3)
+  other = metrics.Exporter(rank=4)              # private registries: two exporters in one process
+  log = metrics.StepLogger(str(tmp_path / "m.jsonl"), rank=3, exporter=exp)
+  log.log(step=7, loss=0.25, images_per_s=13428.0, note="text fields are skipped", ok=True)
+  log.log(step=8, loss=0.125, **{"h2d MB/s": 1400.5})
+  body = urllib.request.urlopen(exp.url(), timeout=5).read().decode()
+  assert 'tfos_loss{rank="3"} 0.125' in body and 'tfos_step{rank="3"} 8.0' in body
+  assert 'tfos_images_per_s{rank="3"} 13428.0' in body and 'tfos_h2d_MB_s{rank="3"} 1400.5' in body
+  assert "tfos_last_log_timestamp_seconds" in body and "tfos_note" not in body and "tfos_ok" not in body
+  assert "tfos_loss" not in urllib.request.urlopen(other.url(), timeout=5).read().decode()
+  assert [r["step"] for r in metrics.read(log.path)] == [7, 8]      # the JSONL side is unchanged
+  log.close()
+  exp.close()
+  other.close()
