@@ -18,5 +18,6 @@ setup(
     extras_require={"spark": ["pyspark>=3.1"], "test": ["pytest", "pytest-timeout"]},
     entry_points={"console_scripts": [
         "tfos-b200-inference=tensorflowonspark_b200.inference:main",
+        "tfos-b200=tensorflowonspark_b200.__main__:main",
     ]},
 )

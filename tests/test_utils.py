@@ -336,3 +336,26 @@ def test_prometheus_exporter_serves_what_the_step_logger_logs(tmp_path):
   log.close()
   exp.close()
   other.close()
+
+
+def test_package_cli_info_env_and_stop_streaming(capsys, monkeypatch):
+  """python -m tensorflowonspark_b200: info / env / stop-streaming (reference
+  examples/utils/stop_streaming.py sends STOP to the reservation server of a streaming job)."""
+  import json
+  from tensorflowonspark_b200 import __main__ as cli, reservation
+  assert cli.main(["info"]) == 0
+  info = json.loads(capsys.readouterr().out)
+  assert info["torch"] == torch.__version__ and "extension" in info and isinstance(info["gpus"], (list, str))
+  monkeypatch.setenv("TFOS_NVLS", "0")
+  assert cli.main(["env"]) == 0 and "TFOS_NVLS=0" in capsys.readouterr().out
+  server = reservation.Server(1)
+  host, port = server.start()
+  assert not server.done
+  assert cli.main(["stop-streaming", host, str(port)]) == 0
+  deadline = __import__("time").time() + 5
+  while not server.done and __import__("time").time() < deadline:
+    __import__("time").sleep(0.05)
+  assert server.done
+  server.stop()
+  assert cli.main(["stop-streaming", "onlyhost"]) == 2 and cli.main(["no-such-command"]) == 2
+  assert cli.main([]) == 0 and "stop-streaming HOST PORT" in capsys.readouterr().out
