@@ -100,3 +100,84 @@ def test_stem_geometry_matches_a_7x7_stride2_pad3_convolution():
     OH, OW, Wp = igemm.stem_geometry(hw, hw)
     assert OH == (hw + 6 - 7) // 2 + 1 == OW
     assert Wp % 2 == 0 and Wp >= hw + 4 and Wp >= 2 * (OW - 1) + 8   # last window stays in the row
+
+
+_spec_entry = st.one_of(
+    st.tuples(st.just("int64"), st.integers(1, 6), st.sampled_from(["int64", "int32", "uint8"])),
+    st.tuples(st.just("float"), st.integers(1, 6), st.just("float32")),
+    st.tuples(st.just("bytes"), st.integers(1, 9), st.just("uint8")),
+)
+
+
+@settings(max_examples=80, deadline=None)
+@given(st.dictionaries(_names, _spec_entry, min_size=1, max_size=5), st.integers(1, 7), st.randoms(use_true_random=False))
+def test_decode_batch_agrees_with_the_per_record_decoder_for_any_spec(spec, n, rnd):
+  """tfrecord.decode_batch (native, one pass into dense arrays) == stacking decode_example."""
+  recs, want = [], {k: [] for k in spec}
+  for _ in range(n):
+    feats = {}
+    for name, (kind, length, dt) in spec.items():
+      if kind == "int64":
+        hi = {"int64": 2 ** 62, "int32": 2 ** 31 - 1, "uint8": 255}[dt]
+        lo = {"int64": -2 ** 62, "int32": -2 ** 31, "uint8": 0}[dt]
+        vals = [rnd.randint(lo, hi) for _ in range(length)]
+        feats[name] = ("int64", vals)
+      elif kind == "float":
+        vals = [float(np.float32(rnd.uniform(-1e6, 1e6))) for _ in range(length)]
+        feats[name] = ("float", vals)
+      else:
+        vals = bytes(rnd.randrange(256) for _ in range(length))
+        feats[name] = ("bytes", [vals])
+        vals = list(vals)
+      want[name].append(vals)
+    feats["extra_" + str(len(recs))] = ("int64", [1, 2, 3])        # features nobody asked for
+    recs.append(tfrecord.encode_example(feats))
+  out = tfrecord.decode_batch(recs, {k: v for k, v in spec.items()}, threads=rnd.choice([1, 2]))
+  for name, (kind, length, dt) in spec.items():
+    assert out[name].shape == (n, length) and out[name].dtype == np.dtype(dt)
+    assert np.array_equal(out[name], np.asarray(want[name], dtype=dt))
+
+
+@settings(max_examples=25, deadline=None)
+@given(st.lists(st.tuples(st.sampled_from(["push", "sparse", "pull"]), st.integers(0, 2 ** 31)), min_size=1, max_size=12))
+def test_tcp_parameter_server_matches_a_numpy_model_for_any_request_sequence(ops):
+  """parallel/ps_net.py: whatever order pushes, row-sparse pushes and pulls arrive in, two server
+  slices behind sockets hold what a flat numpy vector would."""
+  from tensorflowonspark_b200 import reservation
+  from tensorflowonspark_b200.parallel import ps_net
+  srv = reservation.Server(1)
+  addr = srv.start()
+  cid = "prop-{}".format(abs(hash(tuple(ops))) % 10 ** 9)
+
+  class Ctx(object):
+    def __init__(self, job, idx):
+      self.job_name, self.task_index = job, idx
+      self.cluster_spec = {"ps": ["10.0.0.1:1", "10.0.0.2:2"], "worker": ["10.0.0.3:3"]}
+      self.cluster_id, self.server_addr, self.gpus = cid, addr, []
+
+  numel, width, base = 56, 5, 3
+  servers = [ps_net.NetPSServer(Ctx("ps", i), numel) for i in range(2)]
+  client = ps_net.NetPSClient(Ctx("worker", 0))
+  model = np.zeros(numel, np.float32)
+  try:
+    for op, seed in ops:
+      rng = np.random.RandomState(seed)
+      if op == "push":
+        g, lr = rng.randn(numel).astype(np.float32), float(rng.rand())
+        client.push(g, lr=lr, scale=0.5)
+        model -= np.float32(lr * 0.5) * g
+      elif op == "sparse":
+        rows = rng.randn(3, width).astype(np.float32)
+        idx = rng.randint(0, (numel - base) // width, 3)
+        client.push_sparse(rows, idx, width=width, base=base, lr=0.25)
+        for row, r in zip(rows, idx):
+          model[base + r * width:base + (r + 1) * width] -= np.float32(0.25) * row
+      else:
+        assert np.allclose(client.pull(), model, atol=1e-5)
+    assert np.allclose(client.pull(), model, atol=1e-5)
+    assert np.allclose(np.concatenate([s_.values() for s_ in servers]), model, atol=1e-5)
+  finally:
+    client.close()
+    for s_ in servers:
+      s_.close()
+    srv.stop()
