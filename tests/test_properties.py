@@ -110,7 +110,8 @@ _spec_entry = st.one_of(
 
 
 @settings(max_examples=80, deadline=None)
-@given(st.dictionaries(_names, _spec_entry, min_size=1, max_size=5), st.integers(1, 7), st.randoms(use_true_random=False))
+@given(st.dictionaries(_names, _spec_entry, min_size=1, max_size=5), st.integers(1, 7),
+       st.randoms(use_true_random=False))
 def test_decode_batch_agrees_with_the_per_record_decoder_for_any_spec(spec, n, rnd):
   """tfrecord.decode_batch (native, one pass into dense arrays) == stacking decode_example."""
   recs, want = [], {k: [] for k in spec}
@@ -139,7 +140,8 @@ def test_decode_batch_agrees_with_the_per_record_decoder_for_any_spec(spec, n, r
 
 
 @settings(max_examples=25, deadline=None)
-@given(st.lists(st.tuples(st.sampled_from(["push", "sparse", "pull"]), st.integers(0, 2 ** 31)), min_size=1, max_size=12))
+@given(st.lists(st.tuples(st.sampled_from(["push", "sparse", "pull"]), st.integers(0, 2 ** 31)),
+                min_size=1, max_size=12))
 def test_tcp_parameter_server_matches_a_numpy_model_for_any_request_sequence(ops):
   """parallel/ps_net.py: whatever order pushes, row-sparse pushes and pulls arrive in, two server
   slices behind sockets hold what a flat numpy vector would."""
