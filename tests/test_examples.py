@@ -131,14 +131,15 @@ def test_streaming_feed_with_async_parameter_server_stops_on_terminate(mnist, tm
                         "--images_labels", str(watched), "--max_examples", "256", "--interval", "0.3"],
                        cwd=ROOT, env=env, stdout=log, stderr=subprocess.STDOUT)
   try:
-    time.sleep(5)                                        # cluster up, stream started
+    time.sleep(4)                                        # cluster up, stream (probably) started
     parts = sorted(f for f in os.listdir(mnist + "/data/csv/train") if f.startswith("part-"))
-    for i, name in enumerate(parts):                     # files appearing in the watched directory
-      if p.poll() is not None:
+    for i in range(90):                                  # new files keep appearing until the job ends:
+      if p.poll() is not None:                           # a slow start only delays the first batch
         break
-      shutil.copy(os.path.join(mnist, "data/csv/train", name), str(watched / "f{}.csv".format(i)))
+      shutil.copy(os.path.join(mnist, "data/csv/train", parts[i % len(parts)]),
+                  str(watched / "f{}.csv".format(i)))
       time.sleep(1)
-    rc = p.wait(timeout=120)
+    rc = p.wait(timeout=60)
   finally:
     if p.poll() is None:
       p.kill()
