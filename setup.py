@@ -15,7 +15,8 @@ setup(
     package_data={"tensorflowonspark_b200": ["_ext/*.so"]},
     python_requires=">=3.10",
     install_requires=["torch>=2.6", "numpy", "cloudpickle", "msgpack", "pybind11", "ninja"],
-    extras_require={"spark": ["pyspark>=3.1"], "test": ["pytest", "pytest-timeout"]},
+    extras_require={"spark": ["pyspark>=3.1"], "remote_fs": ["pyarrow"], "metrics": ["prometheus_client"],
+                    "test": ["pytest", "pytest-timeout", "hypothesis", "protobuf"]},
     entry_points={"console_scripts": [
         "tfos-b200-inference=tensorflowonspark_b200.inference:main",
         "tfos-b200=tensorflowonspark_b200.__main__:main",
