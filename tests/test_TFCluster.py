@@ -220,3 +220,45 @@ def test_gradient_comm_falls_back_to_the_process_group_without_gpus(sc):
   res = [json.load(open("{}/{}".format(d, r))) for r in range(2)]
   for r, rec in enumerate(res):
     assert rec == {"kind": "GroupComm", "world": 2, "rank": r, "single_host": True, "w": 5.0, "g": 3.0}
+
+
+def test_gradient_comm_builds_the_two_level_communicator_for_workers_on_different_hosts(sc):
+  """ctx.gradient_comm() on a cluster whose workers registered from two hosts, one GPU each: the
+  selection logic, the per-local-index process groups and HierComm's collectives, with the GPU
+  and the second host faked (gloo on CPU; the kernels' side is tools/gpu_check_hier.py)."""
+  import tempfile
+  d = tempfile.mkdtemp()
+
+  def fn(args, ctx):
+    import json
+    import torch
+    from tensorflowonspark_b200 import TFSparkNode
+    ctx.init_process_group(backend="gloo")                    # (a GPU node would get NCCL)
+    ctx.gpus = [0]
+    ctx.worker_hosts = lambda: ["host-a", "host-b"]           # one worker per "host"
+    real_avail, real_dev = torch.cuda.is_available, TFSparkNode.TFNodeContext.device
+    torch.cuda.is_available = lambda: True
+    TFSparkNode.TFNodeContext.device = property(lambda self: torch.device("cpu"))
+    try:
+      assert not ctx.single_host
+      comm = ctx.gradient_comm()
+    finally:
+      torch.cuda.is_available, TFSparkNode.TFNodeContext.device = real_avail, real_dev
+    w = comm.alloc("weights", 8, torch.float32)
+    w.fill_(float(ctx.rank + 5))
+    comm.broadcast("weights", root=0)
+    g = torch.full((8,), float(ctx.rank + 1))
+    comm.all_reduce_inter(g)
+    comm.barrier()
+    with open("{}/{}".format(args["d"], ctx.rank), "w") as f:
+      json.dump({"kind": type(comm).__name__, "hosts": comm.hosts, "local_world": comm.local_world,
+                 "local_rank": comm.local_rank, "world": comm.world, "w": float(w[0]), "g": float(g[0])}, f)
+
+  cluster = TFCluster.run(sc, fn, {"d": d}, 2, 0, input_mode=TFCluster.InputMode.TENSORFLOW,
+                          master_node="chief")
+  cluster.shutdown()
+  import json
+  for r in range(2):
+    rec = json.load(open("{}/{}".format(d, r)))
+    assert rec == {"kind": "HierComm", "hosts": 2, "local_world": 1, "local_rank": 0, "world": 2,
+                   "w": 5.0, "g": 3.0}
