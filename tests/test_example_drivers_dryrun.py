@@ -140,3 +140,27 @@ def test_resnet_cifar_entry_points_share_main_fun_and_local_context(fake_gpu, tm
   assert _Trainer.made[-1].kw["comm"] is None                                # --ds off: no collective
   img = __import__("numpy").zeros((4, 32, 32, 3), dtype="uint8")
   assert mod.augment(img, __import__("numpy").random.RandomState(0)).shape == img.shape
+
+
+def test_segmentation_spark_driver_tf_mode_with_a_communicator(fake_gpu, monkeypatch):
+  from tensorflowonspark_b200.models import unet
+  monkeypatch.setattr(unet, "UNetTrainer", _Trainer)
+  monkeypatch.syspath_prepend(os.path.join(ROOT, "examples", "segmentation"))
+  sys.modules.pop("segmentation_spark", None)
+  mod = importlib.import_module("segmentation_spark")
+
+  class Args(object):
+    batch_size, learning_rate, input_mode, steps, epochs, num_examples = 4, 1e-3, "tf", 12, 1, 64
+
+  real_batch = _Trainer.synthetic_batch
+  monkeypatch.setattr(_Trainer, "synthetic_batch",
+                      lambda self, seed=0: (torch.zeros(4, 8, 8, 3, dtype=torch.uint8), None))
+  comm = _Comm()
+  ctx = _Ctx(world=2, comm=comm)
+  ctx.num_workers = 2
+  mod.main_fun(Args(), ctx)
+  net = _Trainer.made[-1]
+  assert net.kw["comm"] is comm and net.kw["classes"] == 3 and net.captured and net.steps == 1 + 12
+  assert comm.broadcasts == [("weights", 0), ("aux32", 0)]
+  assert real_batch is not _Trainer.synthetic_batch
+  sys.modules.pop("segmentation_spark", None)
