@@ -104,6 +104,30 @@ def _slot_layout(n, num_clients, cuda):
   return lay
 
 
+def apply_numpy(master, state1, state2, hyper, g, lo, decay_end, ema_begin, opt):
+  """One server-side optimizer step on host arrays - the twin of ps_apply_kernel (csrc/
+  optim_comm.cu): ``g`` is the received slice for global elements [lo, lo + len(g)); elements at or
+  beyond ``ema_begin`` are the non-trainable tail (``w -= g``: running-statistics deltas), the
+  rest get gradient scale hyper[3], L2 on the elements below ``decay_end``, then SGD / momentum /
+  Adam (``opt`` 0 / 1 / 2; Adam advances its step count hyper[7])."""
+  h = hyper
+  idx = np.arange(lo, lo + g.size)
+  tr, ema = idx < ema_begin, idx >= ema_begin
+  w = master
+  w[ema] -= g[ema]
+  gg = g[tr] * h[3]
+  gg = gg + h[2] * w[tr] * (idx[tr] < decay_end)
+  if opt == 1:
+    state1[tr] = h[1] * state1[tr] + gg
+    gg = state1[tr]
+  elif opt == 2:
+    h[7] += 1.0
+    state1[tr] = h[4] * state1[tr] + (1 - h[4]) * gg
+    state2[tr] = h[5] * state2[tr] + (1 - h[5]) * gg * gg
+    gg = (state1[tr] / (1 - h[4] ** h[7])) / (np.sqrt(state2[tr] / (1 - h[5] ** h[7])) + h[6])
+  w[tr] -= h[0] * gg
+
+
 class PSServer(object):
   """Runs inside a 'ps' node: hosts parameters [lo, hi) of the flat vector."""
 
@@ -223,24 +247,8 @@ class PSServer(object):
           "applied_flag": self.applied.data_ptr() + 4 * k, "seq": int(seq),
           "block_counter": self.base + self.layout["counter"], "opt": self.opt})
     else:
-      h = self.hyper
-      g = self.slots[k * n:(k + 1) * n].copy()
-      idx = np.arange(self.lo, self.hi)
-      tr, ema = idx < self.ema_begin, idx >= self.ema_begin
-      w = self.master
-      w[ema] -= g[ema]
-      gg = g[tr] * h[3]
-      gg = gg + h[2] * w[tr] * (idx[tr] < self.decay_end)
-      if self.opt == 1:
-        self.state1[tr] = h[1] * self.state1[tr] + gg
-        gg = self.state1[tr]
-      elif self.opt == 2:
-        h[7] += 1.0
-        self.state1[tr] = h[4] * self.state1[tr] + (1 - h[4]) * gg
-        self.state2[tr] = h[5] * self.state2[tr] + (1 - h[5]) * gg * gg
-        gg = (self.state1[tr] / (1 - h[4] ** h[7])) / (
-            np.sqrt(self.state2[tr] / (1 - h[5] ** h[7])) + h[6])
-      w[tr] -= h[0] * gg
+      apply_numpy(self.master, self.state1, self.state2, self.hyper,
+                  self.slots[k * n:(k + 1) * n].copy(), self.lo, self.decay_end, self.ema_begin, self.opt)
       self.applied[k] = seq
     self._applied_host[k] = int(seq)
     self.applies += 1

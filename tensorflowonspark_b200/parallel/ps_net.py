@@ -265,23 +265,8 @@ class NetPSServer(object):
           "block_counter": self._counter.data_ptr(), "opt": self.opt})
       torch.cuda.current_stream().synchronize()   # the staging buffer is reused by the next push
     else:
-      h = self.hyper
-      idx = np.arange(self.lo, self.hi)
-      tr, ema = idx < self.ema_begin, idx >= self.ema_begin
-      w = self.master
-      w[ema] -= g[ema]
-      gg = g[tr] * h[3]
-      gg = gg + h[2] * w[tr] * (idx[tr] < self.decay_end)
-      if self.opt == 1:
-        self.state1[tr] = h[1] * self.state1[tr] + gg
-        gg = self.state1[tr]
-      elif self.opt == 2:
-        h[7] += 1.0
-        self.state1[tr] = h[4] * self.state1[tr] + (1 - h[4]) * gg
-        self.state2[tr] = h[5] * self.state2[tr] + (1 - h[5]) * gg * gg
-        gg = (self.state1[tr] / (1 - h[4] ** h[7])) / (
-            np.sqrt(self.state2[tr] / (1 - h[5] ** h[7])) + h[6])
-      w[tr] -= h[0] * gg
+      _ps.apply_numpy(self.master, self.state1, self.state2, self.hyper, g, self.lo, self.decay_end,
+                      self.ema_begin, self.opt)
     self.applies += 1
 
   # ------------------------------------------------------------------ PSServer surface
